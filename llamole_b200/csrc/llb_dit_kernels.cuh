@@ -1,0 +1,660 @@
+// Device kernels of the GraphDiT sampler that are not GEMMs: token one-hot builder, QKV epilogue (per-head
+// LayerNorm), small-sequence attention on mma.sync, and the fused per-molecule step kernel
+// (output-layer LN/modulate/symmetrise -> softmax -> closed-form posterior -> guidance -> categorical sample).
+#pragma once
+#include "llb_common.cuh"
+
+namespace llb {
+
+constexpr int DIT_XC = 16;  // atom classes
+constexpr int DIT_EC = 5;   // bond classes
+constexpr int DIT_DH = 64;  // head dim (fixed)
+constexpr int DIT_MAXN = 64;
+
+// ------------------------------------------------------------------------------------------------
+// QKV GEMM epilogue: per-head affine LayerNorm on q and k (layers.py:49-50,66), softmax scale folded into q.
+// ------------------------------------------------------------------------------------------------
+struct EpiQKV {
+  static constexpr int CHUNK = 64;
+  __nv_bfloat16* out;  // (M, 3H)
+  int ld, H;
+  const float *qw, *qb, *kw, *kb;  // (64) each
+  float q_scale;                   // dh^-0.5 * log2(e)
+  __device__ __forceinline__ void operator()(int row, int col0, const float* acc, int M, int N) const {
+    const int which = col0 / H;  // 0 q, 1 k, 2 v
+    float v[64];
+    if (which < 2) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) s += acc[i];
+      const float mean = s * (1.0f / 64.0f);
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        const float d = acc[i] - mean;
+        q = fmaf(d, d, q);
+      }
+      const float rstd = rsqrtf(q * (1.0f / 64.0f) + 1e-5f);
+      const float* w = which == 0 ? qw : kw;
+      const float* b = which == 0 ? qb : kb;
+      const float post = which == 0 ? q_scale : 1.0f;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) v[i] = ((acc[i] - mean) * rstd * __ldg(w + i) + __ldg(b + i)) * post;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 64; ++i) v[i] = acc[i];
+    }
+    __nv_bfloat16* o = out + (size_t)row * ld + col0;
+#pragma unroll
+    for (int i = 0; i < 64; i += 8)
+      *reinterpret_cast<uint4*>(o + i) = make_uint4(pack_bf16x2(v[i], v[i + 1]), pack_bf16x2(v[i + 2], v[i + 3]),
+                                                    pack_bf16x2(v[i + 4], v[i + 5]), pack_bf16x2(v[i + 6], v[i + 7]));
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Token builder: one-hot joint rows [X_t | E_t row] for the valid tokens (transformer.py:94-95).
+// tok (Mtok, K0) bf16; one warp per token.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dit_tokens_kernel(const int8_t* __restrict__ X, const int8_t* __restrict__ E,
+                                                         const int32_t* __restrict__ mol_off, const int32_t* __restrict__ row_mol,
+                                                         __nv_bfloat16* __restrict__ tok, int Mtok, int N, int K0) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= Mtok) return;
+  const int b = row_mol[r];
+  const int i = r - mol_off[b];
+  const int n = mol_off[b + 1] - mol_off[b];
+  const int xt = X[(size_t)b * N + i];
+  const int8_t* erow = E + ((size_t)b * N + i) * N;
+  __nv_bfloat16* o = tok + (size_t)r * K0;
+  const __nv_bfloat16 one = __float2bfloat16(1.0f), zero = __float2bfloat16(0.0f);
+  for (int k = lane; k < K0; k += 32) {
+    bool hot = false;
+    if (k < DIT_XC) {
+      hot = (k == xt);
+    } else {
+      const int j = (k - DIT_XC) / DIT_EC, a = (k - DIT_XC) % DIT_EC;
+      if (j < n) hot = (erow[j] == a);
+    }
+    o[k] = hot ? one : zero;
+  }
+}
+
+// c (B+1, H) bf16 = timestep table row t + step-invariant part (cond rows) / drop vector (last row).
+__global__ void dit_cvec_kernel(const float* __restrict__ c1_t, const float* __restrict__ cinv,
+                                const float* __restrict__ c_unc, __nv_bfloat16* __restrict__ cvec, int B, int H) {
+  const int total = (B + 1) * H;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = i / H, h = i % H;
+    const float v = c1_t[h] + (b < B ? cinv[(size_t)b * H + h] : c_unc[h]);
+    cvec[i] = __float2bfloat16(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Attention over one (sequence, head): n <= 64 tokens, dh = 64 (layers.py:68-81; only valid tokens exist
+// in the packed layout, which is output-identical to the reference's masking).
+// 4 warps, warp w owns query rows [16w, 16w+16).  S = Q K^T and O = P V on mma.sync.m16n8k16 (bf16, fp32 acc).
+// q is pre-scaled by dh^-0.5 * log2(e) so the softmax is exp2(s - max).
+// ------------------------------------------------------------------------------------------------
+constexpr int ATT_LD = 72;  // padded smem row (bf16 elements): conflict-free ldmatrix
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(128) dit_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
+                                                            const int32_t* __restrict__ mol_off, int B, int Mtok, int H) {
+  __shared__ __align__(16) __nv_bfloat16 sQ[64 * ATT_LD];
+  __shared__ __align__(16) __nv_bfloat16 sK[64 * ATT_LD];
+  __shared__ __align__(16) __nv_bfloat16 sV[64 * ATT_LD];
+  const int seq = blockIdx.x;  // pass * B + molecule
+  const int head = blockIdx.y;
+  const int b = seq % B, pass = seq / B;
+  const int row0 = pass * Mtok + mol_off[b];
+  const int n = mol_off[b + 1] - mol_off[b];
+  if (n == 0) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ld = 3 * H;
+  const int npad = (n + 15) & ~15;
+  // load q, k, v head slices (16 B per thread per access); rows >= n are zero
+  for (int idx = tid; idx < npad * 8 * 3; idx += 128) {
+    const int mat = idx / (npad * 8);
+    const int rem = idx % (npad * 8);
+    const int r = rem >> 3, ch = rem & 7;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (r < n) v = *reinterpret_cast<const uint4*>(qkv + (size_t)(row0 + r) * ld + mat * H + head * DIT_DH + ch * 8);
+    __nv_bfloat16* dst = (mat == 0 ? sQ : (mat == 1 ? sK : sV)) + r * ATT_LD + ch * 8;
+    *reinterpret_cast<uint4*>(dst) = v;
+  }
+  __syncthreads();
+  if (warp * 16 >= n) return;
+  const int ntiles = npad >> 3;  // key tiles of 8
+  // ---- S = Q K^T
+  float s[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    uint32_t a0, a1, a2, a3;
+    ldsm_x4(smem_u32(sQ + (warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * ATT_LD + ks * 16 + (lane >> 4) * 8), a0, a1, a2, a3);
+#pragma unroll
+    for (int jp = 0; jp < 4; ++jp) {
+      if (jp * 2 < ntiles) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4(smem_u32(sK + (jp * 16 + (lane & 7) + (lane >> 4) * 8) * ATT_LD + ks * 16 + ((lane >> 3) & 1) * 8), b0, b1, b2, b3);
+        mma_bf16_16816(s[2 * jp], a0, a1, a2, a3, b0, b1);
+        mma_bf16_16816(s[2 * jp + 1], a0, a1, a2, a3, b2, b3);
+      }
+    }
+  }
+  // ---- softmax over keys < n (rows g and g+8 of this warp's 16)
+  const int t4 = lane & 3;
+  float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int key = j * 8 + t4 * 2 + e;
+      if (key >= n) s[j][e] = s[j][2 + e] = -INFINITY;
+      m0 = fmaxf(m0, s[j][e]);
+      m1 = fmaxf(m1, s[j][2 + e]);
+    }
+  }
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+  float l0 = 0.f, l1 = 0.f;
+  uint32_t p[8][2];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float e0 = exp2f(s[j][0] - m0), e1 = exp2f(s[j][1] - m0);
+    const float e2 = exp2f(s[j][2] - m1), e3 = exp2f(s[j][3] - m1);
+    l0 += e0 + e1;
+    l1 += e2 + e3;
+    p[j][0] = pack_bf16x2(e0, e1);
+    p[j][1] = pack_bf16x2(e2, e3);
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  // ---- O = P V
+  float o[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    if (ks * 16 < npad) {
+      const uint32_t a0 = p[2 * ks][0], a1 = p[2 * ks][1], a2 = p[2 * ks + 1][0], a3 = p[2 * ks + 1][1];
+#pragma unroll
+      for (int dp = 0; dp < 4; ++dp) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4_t(smem_u32(sV + (ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * ATT_LD + dp * 16 + (lane >> 4) * 8), b0, b1, b2, b3);
+        mma_bf16_16816(o[2 * dp], a0, a1, a2, a3, b0, b1);
+        mma_bf16_16816(o[2 * dp + 1], a0, a1, a2, a3, b2, b3);
+      }
+    }
+  }
+  const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+  const int g = lane >> 2;
+  const int r0 = warp * 16 + g, r1 = r0 + 8;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int col = head * DIT_DH + j * 8 + t4 * 2;
+    if (r0 < n) *reinterpret_cast<uint32_t*>(out + (size_t)(row0 + r0) * H + col) = pack_bf16x2(o[j][0] * inv0, o[j][1] * inv0);
+    if (r1 < n) *reinterpret_cast<uint32_t*>(out + (size_t)(row0 + r1) * H + col) = pack_bf16x2(o[j][2] * inv1, o[j][3] * inv1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused per-molecule step kernel.
+// ------------------------------------------------------------------------------------------------
+struct DitTablesDev {
+  float x_marg[DIT_XC];
+  float e_marg[DIT_EC];
+  float xe[DIT_XC][DIT_EC];
+  float ex[DIT_EC][DIT_XC];
+};
+
+struct DitStepArgs {
+  // logits source A: raw output-layer rows (M, raw_ld) fp32 + modulation (B+1, 2*d0) fp32
+  const float* raw;
+  int raw_ld;
+  const float* modout;
+  // logits source B: dense masked logits in the reference layout (parity entry)
+  const float *lcX, *lcE, *luX, *luE;
+  const int32_t* mol_off;
+  int B, N, Mtok, passes;
+  // state (in place)
+  int8_t* X;
+  int8_t* E;
+  // schedule scalars for this step
+  float beta_t, abar_s, abar_t, guide_scale;
+  // noise
+  const float* qX;  // (B,N,16) or null
+  const float* qE;  // (B,N,N,5) or null
+  uint64_t seed;
+  uint32_t stream_id;  // counter-RNG stream (= s, the index of the state being produced)
+  int64_t mol_base;
+  // outputs
+  int sample;        // 1: write the new state
+  float* dumpX;      // optional (B,N,16): logits of pass `dump_pass` (sample==0) or guided probs (sample==1)
+  float* dumpE;      // optional (B,N,N,5)
+  int dump_pass;
+  int dump_logits;
+};
+
+// Per-node statistics of one pass kept in shared memory.
+struct NodeStats {
+  float pX[DIT_XC];   // softmax of the atom logits
+  float S[DIT_EC];    // sum_j softmax(E logits)[i,j,:] over all N slots (masked / diagonal slots give 0.2)
+  float A[DIT_EC];    // sum_c pX[c] * xe[c,:]
+};
+
+__device__ __forceinline__ void softmax5(const float* l, float* p) {
+  const float m = fmaxf(fmaxf(fmaxf(l[0], l[1]), fmaxf(l[2], l[3])), l[4]);
+  float e[5], s = 0.f;
+#pragma unroll
+  for (int a = 0; a < 5; ++a) {
+    e[a] = __expf(l[a] - m);
+    s += e[a];
+  }
+  const float inv = 1.0f / s;
+#pragma unroll
+  for (int a = 0; a < 5; ++a) p[a] = e[a] * inv;
+}
+
+// Closed form of reverse_diffusion with Q = a I + (1-a) U (diffusion_utils.py:476-492):
+//   out[k] = ((1-beta) v[k] + beta UX[k]) * (abar_s p[k] + (1-abar_s) PU[k]) / max(abar_t v[k] + (1-abar_t) UX[k], 1e-5)
+__device__ __forceinline__ float post_term(float v, float ux, float p, float pu, float beta, float abar_s, float abar_t) {
+  const float left = (1.0f - beta) * v + beta * ux;
+  const float right = abar_s * p + (1.0f - abar_s) * pu;
+  const float den = fmaxf(abar_t * v + (1.0f - abar_t) * ux, 1e-5f);
+  return left * right / den;
+}
+
+// Dynamic shared memory: T[pass][n][d0] logits rows (fp32), then NodeStats[pass][n], then small arrays.
+__global__ void __launch_bounds__(256) dit_step_kernel(DitStepArgs a, const __grid_constant__ DitTablesDev tb) {
+  extern __shared__ __align__(16) float sm[];
+  const int b = blockIdx.x;
+  const int N = a.N, d0 = DIT_XC + DIT_EC * N;
+  const int off = a.mol_off[b];
+  const int n = a.mol_off[b + 1] - off;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nthreads = blockDim.x;
+  int8_t* Xg = a.X + (size_t)b * N;
+  int8_t* Eg = a.E + (size_t)b * N * N;
+
+  float* T = sm;                                                       // passes * N * d0
+  NodeStats* stats = reinterpret_cast<NodeStats*>(T + (size_t)a.passes * N * d0);   // passes * N
+  float* cnt = reinterpret_cast<float*>(stats + a.passes * N);         // N * 5
+  int8_t* sX = reinterpret_cast<int8_t*>(cnt + N * DIT_EC);            // N
+  int8_t* sE = sX + ((N + 15) & ~15);                                  // N * N
+
+  if (n == 0) {
+    if (a.sample) {
+      for (int i = tid; i < N; i += nthreads) Xg[i] = -1;
+      for (int i = tid; i < N * N; i += nthreads) Eg[i] = -1;
+    }
+    return;
+  }
+  for (int i = tid; i < N; i += nthreads) sX[i] = Xg[i];
+  for (int i = tid; i < N * N; i += nthreads) sE[i] = Eg[i];
+  __syncthreads();
+
+  // ---------------- logits into T ----------------
+  if (a.raw != nullptr) {
+    // output layer tail (transformer.py:166-187): LN(d0) -> modulate -> + one-hot input -> zero diag/masked -> symmetrise
+    for (int p = 0; p < a.passes; ++p) {
+      const float* shift = a.modout + (size_t)(p == 0 ? b : a.B) * (2 * d0);
+      const float* scale = shift + d0;
+      for (int i = warp; i < n; i += nthreads / 32) {
+        const float* src = a.raw + (size_t)(p * a.Mtok + off + i) * a.raw_ld;
+        float* dst = T + ((size_t)p * N + i) * d0;
+        float s = 0.f;
+        for (int k = lane; k < d0; k += 32) {
+          const float v = src[k];
+          dst[k] = v;
+          s += v;
+        }
+        const float mean = warp_sum(s) / (float)d0;
+        float q = 0.f;
+        for (int k = lane; k < d0; k += 32) {
+          const float d = dst[k] - mean;
+          q = fmaf(d, d, q);
+        }
+        const float rstd = rsqrtf(warp_sum(q) / (float)d0 + 1e-5f);
+        for (int k = lane; k < d0; k += 32) dst[k] = (dst[k] - mean) * rstd * (1.0f + scale[k]) + shift[k];
+      }
+    }
+    __syncthreads();
+    // atoms: + one-hot; bonds: symmetrise valid off-diagonal pairs, zero the rest
+    for (int p = 0; p < a.passes; ++p) {
+      float* Tp = T + (size_t)p * N * d0;
+      for (int idx = tid; idx < n * DIT_XC; idx += nthreads) {
+        const int i = idx / DIT_XC, c = idx % DIT_XC;
+        Tp[i * d0 + c] += (sX[i] == c) ? 1.0f : 0.0f;
+      }
+      for (int idx = tid; idx < n * N; idx += nthreads) {
+        const int i = idx / N, j = idx % N;
+        float* tij = Tp + i * d0 + DIT_XC + DIT_EC * j;
+        if (j >= n || j == i) {
+#pragma unroll
+          for (int e = 0; e < DIT_EC; ++e) tij[e] = 0.f;
+        } else if (i < j) {
+          float* tji = Tp + j * d0 + DIT_XC + DIT_EC * i;
+          const int et = sE[i * N + j];
+#pragma unroll
+          for (int e = 0; e < DIT_EC; ++e) {
+            const float m = 0.5f * ((tij[e] + (et == e ? 1.0f : 0.0f)) + (tji[e] + (et == e ? 1.0f : 0.0f)));
+            tij[e] = m;
+            tji[e] = m;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  } else {
+    for (int p = 0; p < a.passes; ++p) {
+      const float* lX = (p == 0 ? a.lcX : a.luX) + (size_t)b * N * DIT_XC;
+      const float* lE = (p == 0 ? a.lcE : a.luE) + (size_t)b * N * N * DIT_EC;
+      float* Tp = T + (size_t)p * N * d0;
+      for (int idx = tid; idx < n * d0; idx += nthreads) {
+        const int i = idx / d0, k = idx % d0;
+        Tp[i * d0 + k] = k < DIT_XC ? lX[i * DIT_XC + k] : lE[(size_t)i * N * DIT_EC + (k - DIT_XC)];
+      }
+    }
+    __syncthreads();
+  }
+
+  if (a.dump_logits) {
+    // masked logits in the reference's dense layout (zeros outside the valid block)
+    const float* Tp = T + (size_t)a.dump_pass * N * d0;
+    float* oX = a.dumpX + (size_t)b * N * DIT_XC;
+    float* oE = a.dumpE + (size_t)b * N * N * DIT_EC;
+    for (int idx = tid; idx < N * DIT_XC; idx += nthreads) {
+      const int i = idx / DIT_XC;
+      oX[idx] = i < n ? Tp[i * d0 + idx % DIT_XC] : 0.f;
+    }
+    for (int idx = tid; idx < N * N * DIT_EC; idx += nthreads) {
+      const int i = idx / (N * DIT_EC), k = idx % (N * DIT_EC);
+      oE[idx] = (i < n && k / DIT_EC < n) ? Tp[i * d0 + DIT_XC + k] : 0.f;
+    }
+    if (!a.sample) return;
+  }
+
+  // ---------------- per-node statistics ----------------
+  // cnt_i[e] = number of slots j with E_t[i,j] == e (masked slots and the z_T diagonal hold no class)
+  for (int idx = tid; idx < n * DIT_EC; idx += nthreads) {
+    const int i = idx / DIT_EC, e = idx % DIT_EC;
+    int c = 0;
+    for (int j = 0; j < n; ++j) c += (sE[i * N + j] == e);
+    cnt[idx] = (float)c;
+  }
+  for (int idx = warp; idx < a.passes * n; idx += nthreads / 32) {
+    const int p = idx / n, i = idx % n;
+    const float* ti = T + ((size_t)p * N + i) * d0;
+    NodeStats& st = stats[p * N + i];
+    // atom softmax (16 logits: lanes 0..15)
+    float l = lane < DIT_XC ? ti[lane] : -INFINITY;
+    const float m = warp_max(l);
+    const float e = lane < DIT_XC ? __expf(l - m) : 0.f;
+    const float sum = warp_sum(e);
+    const float px = e / sum;
+    if (lane < DIT_XC) st.pX[lane] = px;
+    // S over all N slots: valid off-diagonal slots from the logits, the others contribute 0.2 each
+    float Sa[DIT_EC] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int j = lane; j < n; j += 32) {
+      if (j != i) {
+        float pe[DIT_EC];
+        softmax5(ti + DIT_XC + DIT_EC * j, pe);
+#pragma unroll
+        for (int q = 0; q < DIT_EC; ++q) Sa[q] += pe[q];
+      }
+    }
+    const float rest = 0.2f * (float)(N - n + 1);
+#pragma unroll
+    for (int q = 0; q < DIT_EC; ++q) {
+      const float v = warp_sum(Sa[q]) + rest;
+      if (lane == 0) st.S[q] = v;
+    }
+#pragma unroll
+    for (int q = 0; q < DIT_EC; ++q) {
+      const float v = warp_sum(lane < DIT_XC ? px * tb.xe[lane][q] : 0.f);
+      if (lane == 0) st.A[q] = v;
+    }
+  }
+  __syncthreads();
+
+  const float beta = a.beta_t, as_ = a.abar_s, at_ = a.abar_t, gs = a.guide_scale;
+  const uint2 key = make_uint2((uint32_t)(a.seed & 0xffffffffu), (uint32_t)(a.seed >> 32));
+  const uint32_t molid = (uint32_t)(a.mol_base + b);
+
+  // ---------------- atoms ----------------
+  for (int i = tid; i < n; i += nthreads) {
+    const int xt = sX[i];
+    float prob[DIT_XC];
+    for (int p = 0; p < a.passes; ++p) {
+      const NodeStats& st = stats[p * N + i];
+      float un[DIT_XC], sum = 0.f;
+      float sumpx = 0.f;
+#pragma unroll
+      for (int c = 0; c < DIT_XC; ++c) sumpx += st.pX[c];
+#pragma unroll
+      for (int c = 0; c < DIT_XC; ++c) {
+        float ux = tb.x_marg[xt];
+        float pu = sumpx * tb.x_marg[c];
+#pragma unroll
+        for (int e = 0; e < DIT_EC; ++e) {
+          ux = fmaf(cnt[i * DIT_EC + e], tb.xe[c][e], ux);
+          pu = fmaf(st.S[e], tb.ex[e][c], pu);
+        }
+        un[c] = post_term(xt == c ? 1.0f : 0.0f, ux, st.pX[c], pu, beta, as_, at_);
+        sum += un[c];
+      }
+      if (sum == 0.f) {
+#pragma unroll
+        for (int c = 0; c < DIT_XC; ++c) un[c] = 1e-5f;
+        sum = 1e-5f * DIT_XC;
+      }
+      if (p == 0) {
+#pragma unroll
+        for (int c = 0; c < DIT_XC; ++c) prob[c] = un[c] / sum;
+      } else {
+        float gsum = 0.f;
+#pragma unroll
+        for (int c = 0; c < DIT_XC; ++c) {
+          const float pu_ = un[c] / sum;
+          prob[c] = pu_ * powf(prob[c] / fmaxf(pu_, 1e-5f), gs);
+          gsum += prob[c];
+        }
+        gsum = fmaxf(gsum, 1e-5f);
+#pragma unroll
+        for (int c = 0; c < DIT_XC; ++c) prob[c] /= gsum;
+      }
+    }
+    if (a.dumpX && !a.dump_logits) {
+#pragma unroll
+      for (int c = 0; c < DIT_XC; ++c) a.dumpX[((size_t)b * N + i) * DIT_XC + c] = prob[c];
+    }
+    if (a.sample) {
+      float q[DIT_XC];
+      if (a.qX) {
+#pragma unroll
+        for (int c = 0; c < DIT_XC; ++c) q[c] = a.qX[((size_t)b * N + i) * DIT_XC + c];
+      } else {
+#pragma unroll
+        for (int g = 0; g < DIT_XC / 4; ++g) {
+          const uint4 r = philox4x32_10(make_uint4((uint32_t)i, molid, a.stream_id, (uint32_t)g), key);
+          q[4 * g] = exp1_from_bits(r.x), q[4 * g + 1] = exp1_from_bits(r.y);
+          q[4 * g + 2] = exp1_from_bits(r.z), q[4 * g + 3] = exp1_from_bits(r.w);
+        }
+      }
+      // clamp_min(1e-5) -> (renormalisation does not move the argmax) -> argmax(p / q)  (diffusion_utils.py:392-395)
+      int best = 0;
+      float bv = -1.f;
+#pragma unroll
+      for (int c = 0; c < DIT_XC; ++c) {
+        const float v = fmaxf(prob[c], 1e-5f) / q[c];
+        if (v > bv) bv = v, best = c;
+      }
+      Xg[i] = (int8_t)best;
+    }
+  }
+  if (a.sample) {
+    for (int i = n + tid; i < N; i += nthreads) Xg[i] = -1;
+  }
+
+  // ---------------- bonds: pairs i < j of valid nodes (the reference keeps triu(1) and mirrors it) ----------------
+  const int npairs = n * (n - 1) / 2;
+  for (int pidx = tid; pidx < npairs; pidx += nthreads) {
+    // unrank pidx -> (i, j), i < j
+    int i = (int)((2.0f * n - 1.0f - sqrtf((2.0f * n - 1.0f) * (2.0f * n - 1.0f) - 8.0f * (float)pidx)) * 0.5f);
+    while (i > 0 && (i * (2 * n - i - 1)) / 2 > pidx) --i;
+    while (((i + 1) * (2 * n - i - 2)) / 2 <= pidx) ++i;
+    const int j = pidx - (i * (2 * n - i - 1)) / 2 + i + 1;
+    const int et = sE[i * N + j];
+    const int xt = sX[i];
+    float cm = 0.f;
+#pragma unroll
+    for (int e = 0; e < DIT_EC; ++e) cm = fmaf(cnt[i * DIT_EC + e], tb.e_marg[e], cm);
+    float prob[DIT_EC];
+    for (int p = 0; p < a.passes; ++p) {
+      const NodeStats& st = stats[p * N + i];
+      float pe[DIT_EC];
+      softmax5(T + ((size_t)p * N + i) * d0 + DIT_XC + DIT_EC * j, pe);
+      const float Ssum = (st.S[0] + st.S[1]) + (st.S[2] + st.S[3]) + st.S[4];
+      float un[DIT_EC], sum = 0.f;
+#pragma unroll
+      for (int e = 0; e < DIT_EC; ++e) {
+        const float ux = tb.ex[e][xt] + cm;
+        const float pu = st.A[e] + Ssum * tb.e_marg[e];
+        un[e] = post_term(et == e ? 1.0f : 0.0f, ux, pe[e], pu, beta, as_, at_);
+        sum += un[e];
+      }
+      if (sum == 0.f) {
+#pragma unroll
+        for (int e = 0; e < DIT_EC; ++e) un[e] = 1e-5f;
+        sum = 1e-5f * DIT_EC;
+      }
+      if (p == 0) {
+#pragma unroll
+        for (int e = 0; e < DIT_EC; ++e) prob[e] = un[e] / sum;
+      } else {
+        float gsum = 0.f;
+#pragma unroll
+        for (int e = 0; e < DIT_EC; ++e) {
+          const float pu_ = un[e] / sum;
+          prob[e] = pu_ * powf(prob[e] / fmaxf(pu_, 1e-5f), gs);
+          gsum += prob[e];
+        }
+        gsum = fmaxf(gsum, 1e-5f);
+#pragma unroll
+        for (int e = 0; e < DIT_EC; ++e) prob[e] /= gsum;
+      }
+    }
+    if (a.dumpE && !a.dump_logits) {
+#pragma unroll
+      for (int e = 0; e < DIT_EC; ++e) a.dumpE[(((size_t)b * N + i) * N + j) * DIT_EC + e] = prob[e];
+    }
+    if (a.sample) {
+      float q[8];
+      if (a.qE) {
+#pragma unroll
+        for (int e = 0; e < DIT_EC; ++e) q[e] = a.qE[(((size_t)b * N + i) * N + j) * DIT_EC + e];
+      } else {
+        const uint32_t pos = (uint32_t)(N + i * N + j);
+        const uint4 r0 = philox4x32_10(make_uint4(pos, molid, a.stream_id, 0u), key);
+        const uint4 r1 = philox4x32_10(make_uint4(pos, molid, a.stream_id, 1u), key);
+        q[0] = exp1_from_bits(r0.x), q[1] = exp1_from_bits(r0.y), q[2] = exp1_from_bits(r0.z), q[3] = exp1_from_bits(r0.w);
+        q[4] = exp1_from_bits(r1.x);
+      }
+      int best = 0;
+      float bv = -1.f;
+#pragma unroll
+      for (int e = 0; e < DIT_EC; ++e) {
+        const float v = fmaxf(prob[e], 1e-5f) / q[e];
+        if (v > bv) bv = v, best = e;
+      }
+      Eg[i * N + j] = (int8_t)best;
+      Eg[j * N + i] = (int8_t)best;
+    }
+  }
+  if (a.sample) {
+    // diagonal of valid nodes: class 0 (triu(1)+transpose leaves 0 there); everything touching a masked node: none
+    for (int idx = tid; idx < N * N; idx += nthreads) {
+      const int i = idx / N, j = idx % N;
+      if (i >= n || j >= n) Eg[idx] = -1;
+      else if (i == j) Eg[idx] = 0;
+    }
+  }
+}
+
+// z_T from the limit marginals (diffusion_utils.py:495-518): argmax(marg / q); strict upper triangle mirrored,
+// diagonal and masked entries hold no class (-1).
+__global__ void __launch_bounds__(256) dit_init_state_kernel(int8_t* __restrict__ X, int8_t* __restrict__ E,
+                                                             const int32_t* __restrict__ mol_off, int N, const float* __restrict__ qX0,
+                                                             const float* __restrict__ qE0, uint64_t seed, uint32_t stream_id,
+                                                             int64_t mol_base, const __grid_constant__ DitTablesDev tb) {
+  const int b = blockIdx.x;
+  const int n = mol_off[b + 1] - mol_off[b];
+  const uint2 key = make_uint2((uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32));
+  const uint32_t molid = (uint32_t)(mol_base + b);
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    int best = -1;
+    if (i < n) {
+      float bv = -1.f;
+      for (int g = 0; g < DIT_XC / 4; ++g) {
+        float q[4];
+        if (qX0) {
+          for (int e = 0; e < 4; ++e) q[e] = qX0[((size_t)b * N + i) * DIT_XC + 4 * g + e];
+        } else {
+          const uint4 r = philox4x32_10(make_uint4((uint32_t)i, molid, stream_id, (uint32_t)g), key);
+          q[0] = exp1_from_bits(r.x), q[1] = exp1_from_bits(r.y), q[2] = exp1_from_bits(r.z), q[3] = exp1_from_bits(r.w);
+        }
+        for (int e = 0; e < 4; ++e) {
+          const float v = tb.x_marg[4 * g + e] / q[e];
+          if (v > bv) bv = v, best = 4 * g + e;
+        }
+      }
+    }
+    X[(size_t)b * N + i] = (int8_t)best;
+  }
+  for (int idx = threadIdx.x; idx < N * N; idx += blockDim.x) {
+    const int i = idx / N, j = idx % N;
+    if (i >= n || j >= n || i == j) {
+      E[(size_t)b * N * N + idx] = -1;
+    } else if (i < j) {
+      float q[8];
+      if (qE0) {
+        for (int e = 0; e < DIT_EC; ++e) q[e] = qE0[(((size_t)b * N + i) * N + j) * DIT_EC + e];
+      } else {
+        const uint32_t pos = (uint32_t)(N + i * N + j);
+        const uint4 r0 = philox4x32_10(make_uint4(pos, molid, stream_id, 0u), key);
+        const uint4 r1 = philox4x32_10(make_uint4(pos, molid, stream_id, 1u), key);
+        q[0] = exp1_from_bits(r0.x), q[1] = exp1_from_bits(r0.y), q[2] = exp1_from_bits(r0.z), q[3] = exp1_from_bits(r0.w);
+        q[4] = exp1_from_bits(r1.x);
+      }
+      int best = 0;
+      float bv = -1.f;
+      for (int e = 0; e < DIT_EC; ++e) {
+        const float v = tb.e_marg[e] / q[e];
+        if (v > bv) bv = v, best = e;
+      }
+      E[(size_t)b * N * N + i * N + j] = (int8_t)best;
+      E[(size_t)b * N * N + j * N + i] = (int8_t)best;
+    }
+  }
+}
+
+}  // namespace llb

@@ -1,0 +1,706 @@
+// GIN message passing: GraphCLIP encoder and GNNRetrosynthsizer predictor.
+// Reference: graph_encoder/model.py:37-41,124-205; graph_predictor/model.py:306-353,387-423.
+//
+// Data layout in HBM: nodes are rows of (n,H) matrices -- h (fp32 master: residual, self term, pooling) and hb
+// (bf16 copy: the gather source of the aggregation and nothing else).  Edges are a destination-sorted CSR
+// (rowptr/col/etype), graphs are contiguous node ranges (graph_ptr), so every reduction (neighbour sum,
+// per-graph max / sum pooling) is a segmented loop with no atomics.
+#include <vector>
+
+#include "llb_gemm.cuh"
+#include "llb_rowops.cuh"
+
+namespace llb {
+namespace {
+
+constexpr int ATOM_VOCAB = 118;
+constexpr int BOND_VOCAB = 5;
+
+struct GinLayout {
+  int H, L, predictor, out_dim, tdim, HH, HO;
+  std::vector<size_t> mlp0_w, mlp4_w, vn0_w, vn4_w, adapter_w;   // bf16
+  size_t head0_w, head4_w;
+  size_t atom_emb, vn_emb, text_drop;                             // fp32
+  std::vector<size_t> eps, mlp0_b, mlp_ln_w, mlp_ln_b, mlp4_b, bond_emb, norm_w, norm_b;
+  std::vector<size_t> vn0_b, vn_ln_w, vn_ln_b, vn4_b, adapter_b;
+  size_t head0_b, head_ln_w, head_ln_b, head4_b;
+  size_t total;
+};
+
+int make_layout(const llb_gin_config& c, GinLayout& G) {
+  LLB_CHECK_ARG(c.hidden > 0 && c.hidden % 64 == 0, "gin: hidden=%d must be a positive multiple of 64", c.hidden);
+  LLB_CHECK_ARG(c.layers >= 2, "gin: layers=%d must be >= 2 (reference raises ValueError too)", c.layers);
+  LLB_CHECK_ARG(!c.predictor || (c.out_dim >= 1 && c.text_dim > 0 && c.text_dim % 8 == 0), "gin: bad predictor out_dim/text_dim");
+  G.H = c.hidden, G.L = c.layers, G.predictor = c.predictor ? 1 : 0, G.out_dim = c.out_dim, G.tdim = c.text_dim;
+  G.HH = G.predictor ? 4 * G.H : G.H;
+  G.HO = G.predictor ? G.out_dim : G.H;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    off = align_up(off, 256);
+    size_t o = off;
+    off += bytes;
+    return o;
+  };
+  const size_t H = G.H;
+  for (int l = 0; l < G.L; ++l) {
+    G.mlp0_w.push_back(take(4 * H * H * 2));
+    G.mlp4_w.push_back(take(4 * H * H * 2));
+    if (l < G.L - 1) {
+      G.vn0_w.push_back(take(4 * H * H * 2));
+      G.vn4_w.push_back(take(4 * H * H * 2));
+    }
+    if (G.predictor) G.adapter_w.push_back(take(3 * H * (size_t)G.tdim * 2));
+  }
+  G.head0_w = take((size_t)G.HH * H * 2);
+  G.head4_w = take((size_t)G.HO * G.HH * 2);
+  G.atom_emb = take(ATOM_VOCAB * H * 4);
+  G.vn_emb = take(H * 4);
+  G.text_drop = take((size_t)(G.predictor ? G.tdim : 1) * 4);
+  for (int l = 0; l < G.L; ++l) {
+    G.eps.push_back(take(4));
+    G.mlp0_b.push_back(take(4 * H * 4)), G.mlp_ln_w.push_back(take(4 * H * 4)), G.mlp_ln_b.push_back(take(4 * H * 4));
+    G.mlp4_b.push_back(take(H * 4));
+    G.bond_emb.push_back(take(BOND_VOCAB * H * 4));
+    G.norm_w.push_back(take(H * 4)), G.norm_b.push_back(take(H * 4));
+    if (l < G.L - 1) {
+      G.vn0_b.push_back(take(4 * H * 4)), G.vn_ln_w.push_back(take(4 * H * 4)), G.vn_ln_b.push_back(take(4 * H * 4));
+      G.vn4_b.push_back(take(H * 4));
+    }
+    if (G.predictor) G.adapter_b.push_back(take(3 * H * 4));
+  }
+  G.head0_b = take((size_t)G.HH * 4), G.head_ln_w = take((size_t)G.HH * 4), G.head_ln_b = take((size_t)G.HH * 4);
+  G.head4_b = take((size_t)G.HO * 4);
+  G.total = align_up(off, 256);
+  return LLB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Graph preparation
+// ---------------------------------------------------------------------------------------------
+__global__ void gin_prep_nodes_kernel(const int64_t* __restrict__ x, const int64_t* __restrict__ batch, int32_t* __restrict__ x32,
+                                      int32_t* __restrict__ batch32, int32_t* __restrict__ graph_ptr, int n, int B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int xv = (int)x[i];
+  x32[i] = xv < 0 ? 0 : (xv >= ATOM_VOCAB ? ATOM_VOCAB - 1 : xv);
+  const int g = (int)batch[i];
+  batch32[i] = g;
+  const int prev = i == 0 ? -1 : (int)batch[i - 1];
+  for (int k = prev + 1; k <= g; ++k) graph_ptr[k] = i;   // first node of graph k (empty graphs collapse onto i)
+  if (i == n - 1)
+    for (int k = g + 1; k <= B; ++k) graph_ptr[k] = n;
+}
+
+__global__ void gin_degree_kernel(const int64_t* __restrict__ edge_index, int32_t* __restrict__ deg, int e, int n) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= e) return;
+  const int dst = (int)edge_index[(size_t)e + k];
+  if (dst >= 0 && dst < n) atomicAdd(&deg[dst], 1);
+}
+
+// Exclusive scan in three phases (block sums of 1024 elements).
+__global__ void __launch_bounds__(1024) scan_block_kernel(const int32_t* __restrict__ in, int32_t* __restrict__ out,
+                                                          int32_t* __restrict__ block_sums, int n) {
+  __shared__ int32_t wsum[32];
+  const int i = blockIdx.x * 1024 + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int v = i < n ? in[i] : 0;
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = wsum[lane];
+    int wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += t;
+    }
+    wsum[lane] = wi - w;
+    if (lane == 31 && block_sums) block_sums[blockIdx.x] = wi;
+  }
+  __syncthreads();
+  if (i < n) out[i] = incl - v + wsum[warp];
+}
+__global__ void scan_add_kernel(int32_t* __restrict__ out, const int32_t* __restrict__ block_offs, int n) {
+  const int i = blockIdx.x * 1024 + threadIdx.x;
+  if (i < n) out[i] += block_offs[blockIdx.x];
+}
+
+__global__ void gin_fill_kernel(const int64_t* __restrict__ edge_index, const int64_t* __restrict__ edge_attr,
+                                const int32_t* __restrict__ rowptr, int32_t* __restrict__ cursor, int32_t* __restrict__ col,
+                                int32_t* __restrict__ eid, int e, int n) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= e) return;
+  const int src = (int)edge_index[k];
+  const int dst = (int)edge_index[(size_t)e + k];
+  if (dst < 0 || dst >= n) return;
+  const int pos = rowptr[dst] + atomicAdd(&cursor[dst], 1);
+  int a = (int)edge_attr[k];
+  a = a < 0 ? 0 : (a >= BOND_VOCAB ? BOND_VOCAB - 1 : a);
+  col[pos] = (src < 0 || src >= n) ? dst : src;
+  eid[pos] = (k << 3) | a;   // edge id (deterministic order key) with the bond type in the low bits
+}
+// Sort every row by original edge id so that the floating-point summation order is run-to-run deterministic.
+__global__ void gin_sort_rows_kernel(const int32_t* __restrict__ rowptr, int32_t* __restrict__ col, int32_t* __restrict__ eid, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int beg = rowptr[i], end = rowptr[i + 1];
+  for (int a = beg + 1; a < end; ++a) {
+    const int ke = eid[a], kc = col[a];
+    int b = a - 1;
+    while (b >= beg && eid[b] > ke) {
+      eid[b + 1] = eid[b];
+      col[b + 1] = col[b];
+      --b;
+    }
+    eid[b + 1] = ke;
+    col[b + 1] = kc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Node kernels
+// ---------------------------------------------------------------------------------------------
+// h0 = atom_emb[x] + vn_emb (virtual node of layer 0 is the learned row for every graph).
+__global__ void gin_embed_kernel(const int32_t* __restrict__ x32, const float* __restrict__ atom_emb, const float* __restrict__ vn_emb,
+                                 float* __restrict__ h, __nv_bfloat16* __restrict__ hb, int n, int H) {
+  const size_t total = (size_t)n * (H / 4);
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(idx / (H / 4)), c = (int)(idx % (H / 4)) * 4;
+    const float4 a = *reinterpret_cast<const float4*>(atom_emb + (size_t)x32[i] * H + c);
+    const float4 v = *reinterpret_cast<const float4*>(vn_emb + c);
+    const float4 o = make_float4(a.x + v.x, a.y + v.y, a.z + v.z, a.w + v.w);
+    *reinterpret_cast<float4*>(h + (size_t)i * H + c) = o;
+    *reinterpret_cast<uint2*>(hb + (size_t)i * H + c) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+  }
+}
+__global__ void gin_broadcast_rows_kernel(const float* __restrict__ row, float* __restrict__ out, int rows, int W) {
+  const size_t total = (size_t)rows * W;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x)
+    out[idx] = row[idx % W];
+}
+
+// GIN aggregation (graph_encoder/model.py:167-173): out_i = (1+eps) h_i + sum_{j->i} gelu(h_j + bond_emb[e_ji]) -> bf16.
+// One warp per destination node, 8 columns (16 B of bf16) per lane per sweep; CSR rows are short (degree <= ~4).
+__global__ void __launch_bounds__(256) gin_aggregate_kernel(const float* __restrict__ h, const __nv_bfloat16* __restrict__ hb,
+                                                            const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                            const int32_t* __restrict__ eid, const float* __restrict__ bond_emb,
+                                                            const float* __restrict__ eps_ptr, __nv_bfloat16* __restrict__ out,
+                                                            int n, int H) {
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= n) return;
+  const float one_eps = 1.0f + __ldg(eps_ptr);
+  const int beg = rowptr[i], end = rowptr[i + 1];
+  for (int c = lane * 8; c < H; c += 256) {
+    float acc[8];
+    {
+      const float4 a = *reinterpret_cast<const float4*>(h + (size_t)i * H + c);
+      const float4 b = *reinterpret_cast<const float4*>(h + (size_t)i * H + c + 4);
+      acc[0] = one_eps * a.x, acc[1] = one_eps * a.y, acc[2] = one_eps * a.z, acc[3] = one_eps * a.w;
+      acc[4] = one_eps * b.x, acc[5] = one_eps * b.y, acc[6] = one_eps * b.z, acc[7] = one_eps * b.w;
+    }
+    for (int k = beg; k < end; ++k) {
+      const int j = __ldg(col + k);
+      const int et = __ldg(eid + k) & 7;
+      const uint4 u = *reinterpret_cast<const uint4*>(hb + (size_t)j * H + c);
+      const float4 e0 = *reinterpret_cast<const float4*>(bond_emb + (size_t)et * H + c);
+      const float4 e1 = *reinterpret_cast<const float4*>(bond_emb + (size_t)et * H + c + 4);
+      acc[0] += gelu_erf(bf16_lo(u.x) + e0.x), acc[1] += gelu_erf(bf16_hi(u.x) + e0.y);
+      acc[2] += gelu_erf(bf16_lo(u.y) + e0.z), acc[3] += gelu_erf(bf16_hi(u.y) + e0.w);
+      acc[4] += gelu_erf(bf16_lo(u.z) + e1.x), acc[5] += gelu_erf(bf16_hi(u.z) + e1.y);
+      acc[6] += gelu_erf(bf16_lo(u.w) + e1.z), acc[7] += gelu_erf(bf16_hi(u.w) + e1.w);
+    }
+    *reinterpret_cast<uint4*>(out + (size_t)i * H + c) =
+        make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+  }
+}
+
+// Per-graph pooling over the contiguous node range (graph_encoder/model.py:148,152): max -> bf16 operand of the
+// virtual-node MLP, sum -> fp32 (+bf16) read-out.  grid (B, ceil(H/256)).
+__global__ void __launch_bounds__(256) gin_pool_kernel(const float* __restrict__ h, const int32_t* __restrict__ graph_ptr, int H,
+                                                       int is_max, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16) {
+  const int g = blockIdx.x;
+  const int c = blockIdx.y * 256 + threadIdx.x;
+  if (c >= H) return;
+  const int beg = graph_ptr[g], end = graph_ptr[g + 1];
+  float acc = is_max ? -INFINITY : 0.f;
+  for (int i = beg; i < end; ++i) {
+    const float v = h[(size_t)i * H + c];
+    acc = is_max ? fmaxf(acc, v) : acc + v;
+  }
+  if (beg == end) acc = 0.f;
+  if (out_f32) out_f32[(size_t)g * H + c] = acc;
+  if (out_bf16) out_bf16[(size_t)g * H + c] = __float2bfloat16(acc);
+}
+
+// SiLU(c) -> bf16 (adapter operand, graph_predictor/model.py:247-252); c == null broadcasts text_dropping (:315-316).
+__global__ void gin_text_operand_kernel(const float* __restrict__ c, const float* __restrict__ text_drop, __nv_bfloat16* __restrict__ out,
+                                        int B, int W) {
+  const size_t total = (size_t)B * W;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const float v = c ? c[idx] : text_drop[idx % W];
+    out[idx] = __float2bfloat16(silu(v));
+  }
+}
+
+// softmax + top-k of one logits row per CTA (graph_predictor/model.py:177-179).  k selection passes over the
+// L2-resident row; ties resolve to the lowest index like torch.topk's stable behaviour on CPU.
+__global__ void __launch_bounds__(1024) gin_topk_kernel(const float* __restrict__ logits, int ld, int W, int k, float* __restrict__ topv,
+                                                        int32_t* __restrict__ topi) {
+  __shared__ float red_v[32];
+  __shared__ int red_i[32];
+  __shared__ float s_max, s_sum, s_lastv;
+  __shared__ int s_lasti;
+  const float* row = logits + (size_t)blockIdx.x * ld;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float m = -INFINITY;
+  for (int c = tid; c < W; c += 1024) m = fmaxf(m, row[c]);
+  m = warp_max(m);
+  if (lane == 0) red_v[warp] = m;
+  __syncthreads();
+  if (warp == 0) {
+    float x = warp_max(red_v[lane]);
+    if (lane == 0) s_max = x;
+  }
+  __syncthreads();
+  m = s_max;
+  float s = 0.f;
+  for (int c = tid; c < W; c += 1024) s += __expf(row[c] - m);
+  s = warp_sum(s);
+  __syncthreads();
+  if (lane == 0) red_v[warp] = s;
+  __syncthreads();
+  if (warp == 0) {
+    float x = warp_sum(red_v[lane]);
+    if (lane == 0) s_sum = x, s_lastv = INFINITY, s_lasti = -1;
+  }
+  __syncthreads();
+  const float inv = 1.0f / s_sum;
+  for (int r = 0; r < k; ++r) {
+    const float lv = s_lastv;
+    const int li = s_lasti;
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int c = tid; c < W; c += 1024) {
+      const float v = row[c];
+      const bool eligible = (v < lv) || (v == lv && c > li);   // strictly after the previous pick in (value desc, index asc)
+      if (eligible && (v > bv || (v == bv && c < bi))) bv = v, bi = c;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) bv = ov, bi = oi;
+    }
+    __syncthreads();
+    if (lane == 0) red_v[warp] = bv, red_i[warp] = bi;
+    __syncthreads();
+    if (warp == 0) {
+      bv = red_v[lane], bi = red_i[lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) bv = ov, bi = oi;
+      }
+      if (lane == 0) {
+        s_lastv = bv, s_lasti = bi;
+        topv[(size_t)blockIdx.x * k + r] = __expf(bv - m) * inv;
+        topi[(size_t)blockIdx.x * k + r] = bi;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void cost_mlp_kernel(const float* __restrict__ w0, const float* __restrict__ b0, const float* __restrict__ w1,
+                                const float* __restrict__ b1, const float* __restrict__ fps, int fp_dim, int latent,
+                                float* __restrict__ out) {
+  extern __shared__ float hid[];
+  const float* x = fps + (size_t)blockIdx.x * fp_dim;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int o = warp; o < latent; o += nw) {
+    float s = 0.f;
+    for (int k = lane; k < fp_dim; k += 32) s = fmaf(x[k], w0[(size_t)o * fp_dim + k], s);
+    s = warp_sum(s);
+    if (lane == 0) hid[o] = fmaxf(s + b0[o], 0.f);
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float s = 0.f;
+    for (int k = lane; k < latent; k += 32) s = fmaf(hid[k], w1[k], s);
+    s = warp_sum(s);
+    if (lane == 0) out[blockIdx.x] = logf(1.0f + expf(s + b1[0]));
+  }
+}
+
+}  // namespace
+}  // namespace llb
+
+using namespace llb;
+
+struct llb_gin {
+  llb_gin_config cfg;
+  GinLayout G;
+  const uint8_t* blob = nullptr;
+  GemmCounters ctr;
+  int64_t launches = 0;
+  int n = 0, e = 0, B = 0;
+  bool want_logits = false;
+  int32_t *x32 = nullptr, *batch32 = nullptr, *graph_ptr = nullptr, *rowptr = nullptr, *col = nullptr, *eid = nullptr;
+  int32_t *deg = nullptr, *blk = nullptr, *blk2 = nullptr;
+  float* h = nullptr;
+  __nv_bfloat16* hb = nullptr;
+  __nv_bfloat16* agg = nullptr;
+  __nv_bfloat16* z = nullptr;
+  float* u = nullptr;
+  float *vn_cur = nullptr, *vn_next = nullptr, *vu = nullptr;
+  __nv_bfloat16 *pool_b = nullptr, *vz = nullptr;
+  float* mod = nullptr;
+  __nv_bfloat16* ctext = nullptr;
+  float* pooled = nullptr;
+  __nv_bfloat16* pooled_b = nullptr;
+  __nv_bfloat16* hz = nullptr;
+  float* head_out = nullptr;
+  float* logits_ws = nullptr;
+  int chunk_rows = 0;
+  template <class T>
+  const T* w(size_t off) const { return reinterpret_cast<const T*>(blob + off); }
+};
+
+static const int TOPK_CHUNK = 4096;
+
+static int gin_carve(llb_gin* g, void* ws, size_t ws_bytes, int n, int e, int B, bool want_logits, size_t* need) {
+  const GinLayout& G = g->G;
+  const size_t H = G.H;
+  Arena a(ws, ws_bytes);
+  g->x32 = a.take<int32_t>(n), g->batch32 = a.take<int32_t>(n), g->graph_ptr = a.take<int32_t>(B + 1);
+  g->rowptr = a.take<int32_t>(n + 1), g->col = a.take<int32_t>(e > 0 ? e : 1), g->eid = a.take<int32_t>(e > 0 ? e : 1);
+  g->deg = a.take<int32_t>(n + 1);
+  const int nb = ceil_div(n + 1, 1024);
+  g->blk = a.take<int32_t>(nb + 1), g->blk2 = a.take<int32_t>(ceil_div(nb, 1024) + 1);
+  g->h = a.take<float>((size_t)n * H), g->hb = a.take<__nv_bfloat16>((size_t)n * H), g->agg = a.take<__nv_bfloat16>((size_t)n * H);
+  g->z = a.take<__nv_bfloat16>((size_t)n * 4 * H);
+  g->u = a.take<float>((size_t)n * H);
+  g->vn_cur = a.take<float>((size_t)B * H), g->vn_next = a.take<float>((size_t)B * H), g->vu = a.take<float>((size_t)B * H);
+  g->pool_b = a.take<__nv_bfloat16>((size_t)B * H), g->vz = a.take<__nv_bfloat16>((size_t)B * 4 * H);
+  if (G.predictor) {
+    g->mod = a.take<float>((size_t)G.L * B * 3 * H);
+    g->ctext = a.take<__nv_bfloat16>((size_t)B * G.tdim);
+  }
+  g->pooled = a.take<float>((size_t)B * H), g->pooled_b = a.take<__nv_bfloat16>((size_t)B * H);
+  g->hz = a.take<__nv_bfloat16>((size_t)B * G.HH);
+  if (!G.predictor) g->head_out = a.take<float>((size_t)B * H);
+  g->chunk_rows = B < TOPK_CHUNK ? B : TOPK_CHUNK;
+  if (G.predictor && want_logits) g->logits_ws = a.take<float>((size_t)g->chunk_rows * G.out_dim);
+  *need = align_up(a.off, 256);
+  return LLB_OK;
+}
+
+static int gin_scan(llb_gin* g, cudaStream_t s) {
+  // rowptr[0..n] = exclusive scan of deg[0..n] (deg[n] = 0)
+  const int cnt = g->n + 1;
+  const int nb = ceil_div(cnt, 1024);
+  scan_block_kernel<<<nb, 1024, 0, s>>>(g->deg, g->rowptr, g->blk, cnt);
+  LLB_CUDA_OK(cudaGetLastError());
+  if (nb > 1) {
+    const int nb2 = ceil_div(nb, 1024);
+    LLB_CHECK_ARG(nb2 <= 1024, "gin: too many nodes (%d)", g->n);
+    scan_block_kernel<<<nb2, 1024, 0, s>>>(g->blk, g->blk, g->blk2, nb);
+    LLB_CUDA_OK(cudaGetLastError());
+    if (nb2 > 1) {
+      scan_block_kernel<<<1, 1024, 0, s>>>(g->blk2, g->blk2, nullptr, nb2);
+      scan_add_kernel<<<nb2, 1024, 0, s>>>(g->blk, g->blk2, nb);
+      LLB_CUDA_OK(cudaGetLastError());
+      g->launches += 2;
+    }
+    scan_add_kernel<<<nb, 1024, 0, s>>>(g->rowptr, g->blk, cnt);
+    LLB_CUDA_OK(cudaGetLastError());
+    g->launches += 2;
+  }
+  g->launches++;
+  return LLB_OK;
+}
+
+static int gin_mlp4(llb_gin* g, const __nv_bfloat16* in, int rows, size_t w0, size_t b0, size_t lnw, size_t lnb, size_t w4, size_t b4,
+                    int hidden, int out_f, __nv_bfloat16* zbuf, float* out, int out_ld, cudaStream_t s) {
+  // Linear -> LayerNorm(hidden) -> GELU -> Linear  (the 4H MLP of GINConv / virtual node / heads)
+  const int H = g->G.H;
+  LLB_TRY(gemm_bias_act(in, H, g->w<void>(w0), H, g->w<float>(b0), zbuf, hidden, rows, hidden, H, LLB_ACT_NONE, false, s, &g->ctr));
+  RowLnArgs a;
+  a.in = zbuf, a.in_ld = hidden, a.in_bf16 = true, a.rows = rows, a.width = hidden;
+  a.gamma = g->w<float>(lnw), a.beta = g->w<float>(lnb), a.act = LLB_ACT_GELU;
+  a.out_bf16 = zbuf, a.out_bf16_ld = hidden;
+  LLB_TRY(launch_row_ln(a, s));
+  g->launches++;
+  return gemm_bias_act(zbuf, hidden, g->w<void>(w4), hidden, g->w<float>(b4), out, out_ld, rows, out_f, hidden, LLB_ACT_NONE, true, s, &g->ctr);
+}
+
+// Trunk up to the pooled graph vector (B,H).
+static int gin_trunk(llb_gin* g, const float* c, cudaStream_t s) {
+  const GinLayout& G = g->G;
+  const int H = G.H, L = G.L, n = g->n, B = g->B;
+  LLB_CHECK_ARG(n > 0 && B > 0, "gin: no graph batch bound");
+  const int eb = (int)(((size_t)n * (H / 4) + 255) / 256 < 8192 ? ((size_t)n * (H / 4) + 255) / 256 : 8192);
+  gin_embed_kernel<<<eb, 256, 0, s>>>(g->x32, g->w<float>(G.atom_emb), g->w<float>(G.vn_emb), g->h, g->hb, n, H);
+  gin_broadcast_rows_kernel<<<ceil_div(B * H, 256) < 4096 ? ceil_div(B * H, 256) : 4096, 256, 0, s>>>(g->w<float>(G.vn_emb), g->vn_cur, B, H);
+  LLB_CUDA_OK(cudaGetLastError());
+  g->launches += 2;
+  if (G.predictor) {
+    gin_text_operand_kernel<<<ceil_div(B * G.tdim, 256) < 4096 ? ceil_div(B * G.tdim, 256) : 4096, 256, 0, s>>>(
+        c, g->w<float>(G.text_drop), g->ctext, B, G.tdim);
+    LLB_CUDA_OK(cudaGetLastError());
+    g->launches++;
+    for (int l = 0; l < L; ++l)
+      LLB_TRY(gemm_bias_act(g->ctext, G.tdim, g->w<void>(G.adapter_w[l]), G.tdim, g->w<float>(G.adapter_b[l]),
+                            g->mod + (size_t)l * B * 3 * H, 3 * H, B, 3 * H, G.tdim, LLB_ACT_NONE, true, s, &g->ctr));
+  }
+  for (int l = 0; l < L; ++l) {
+    const bool last = (l == L - 1);
+    gin_aggregate_kernel<<<ceil_div(n, 8), 256, 0, s>>>(g->h, g->hb, g->rowptr, g->col, g->eid, g->w<float>(G.bond_emb[l]),
+                                                        g->w<float>(G.eps[l]), g->agg, n, H);
+    LLB_CUDA_OK(cudaGetLastError());
+    g->launches++;
+    if (!last) {
+      // virtual node of the next layer from the max-pool of this layer's INPUT (model.py:148 / :343)
+      gin_pool_kernel<<<dim3(B, ceil_div(H, 256)), 256, 0, s>>>(g->h, g->graph_ptr, H, 1, nullptr, g->pool_b);
+      LLB_CUDA_OK(cudaGetLastError());
+      g->launches++;
+      LLB_TRY(gin_mlp4(g, g->pool_b, B, G.vn0_w[l], G.vn0_b[l], G.vn_ln_w[l], G.vn_ln_b[l], G.vn4_w[l], G.vn4_b[l], 4 * H, H, g->vz,
+                       g->vu, H, s));
+      RowLnArgs a;
+      a.in = g->vu, a.in_ld = H, a.rows = B, a.width = H, a.normalize = false;
+      a.resid = g->vn_cur, a.resid_ld = H, a.out_f32 = g->vn_next, a.out_f32_ld = H;
+      LLB_TRY(launch_row_ln(a, s));
+      g->launches++;
+    }
+    LLB_TRY(gin_mlp4(g, g->agg, n, G.mlp0_w[l], G.mlp0_b[l], G.mlp_ln_w[l], G.mlp_ln_b[l], G.mlp4_w[l], G.mlp4_b[l], 4 * H, H, g->z,
+                     g->u, H, s));
+    RowLnArgs a;
+    a.in = g->u, a.in_ld = H, a.rows = n, a.width = H;
+    a.row_group = g->batch32;
+    if (G.predictor) {
+      const float* mod = g->mod + (size_t)l * B * 3 * H;
+      a.shift = mod, a.scale = mod + H, a.gate = mod + 2 * H, a.mod_ld = 3 * H;
+    } else {
+      a.gamma = g->w<float>(G.norm_w[l]), a.beta = g->w<float>(G.norm_b[l]);
+    }
+    a.act = last ? LLB_ACT_NONE : LLB_ACT_GELU;
+    a.resid = g->h, a.resid_ld = H;
+    if (!last) a.addvec = g->vn_next, a.addvec_ld = H;
+    a.out_f32 = g->h, a.out_f32_ld = H, a.out_bf16 = g->hb, a.out_bf16_ld = H;
+    LLB_TRY(launch_row_ln(a, s));
+    g->launches++;
+    if (!last) std::swap(g->vn_cur, g->vn_next);
+  }
+  gin_pool_kernel<<<dim3(B, ceil_div(H, 256)), 256, 0, s>>>(g->h, g->graph_ptr, H, 0, g->pooled, g->pooled_b);
+  LLB_CUDA_OK(cudaGetLastError());
+  g->launches++;
+  return LLB_OK;
+}
+
+extern "C" {
+
+int llb_gin_packed_bytes(const llb_gin_config* cfg, size_t* bytes) {
+  LLB_CHECK_ARG(cfg && bytes, "llb_gin_packed_bytes: null argument");
+  GinLayout G;
+  LLB_TRY(make_layout(*cfg, G));
+  *bytes = G.total;
+  return LLB_OK;
+}
+
+int llb_gin_pack_weights(const llb_gin_config* cfg, const llb_gin_weights* w, void* packed, size_t packed_bytes,
+                         llb_stream_t stream) {
+  LLB_TRY(require_sm100());
+  LLB_CHECK_ARG(cfg && w && packed, "llb_gin_pack_weights: null argument");
+  GinLayout G;
+  LLB_TRY(make_layout(*cfg, G));
+  if (packed_bytes < G.total) return fail(LLB_ERR_WORKSPACE, "gin: packed blob needs %zu bytes, got %zu", G.total, packed_bytes);
+  cudaStream_t s = (cudaStream_t)stream;
+  uint8_t* base = (uint8_t*)packed;
+  const int H = G.H;
+  auto bf = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(base + off); };
+  auto cp = [&](size_t off, const float* src, size_t n) {
+    return cudaMemcpyAsync(base + off, src, n * 4, cudaMemcpyDeviceToDevice, s);
+  };
+  LLB_CUDA_OK(cp(G.atom_emb, w->atom_emb, (size_t)ATOM_VOCAB * H));
+  LLB_CUDA_OK(cp(G.vn_emb, w->vn_emb, H));
+  for (int l = 0; l < G.L; ++l) {
+    LLB_TRY(launch_f32_to_bf16(w->mlp0_w[l], H, bf(G.mlp0_w[l]), H, 4 * H, H, H, s));
+    LLB_TRY(launch_f32_to_bf16(w->mlp4_w[l], 4 * H, bf(G.mlp4_w[l]), 4 * H, H, 4 * H, 4 * H, s));
+    LLB_CUDA_OK(cp(G.eps[l], w->eps[l], 1));
+    LLB_CUDA_OK(cp(G.mlp0_b[l], w->mlp0_b[l], 4 * H));
+    LLB_CUDA_OK(cp(G.mlp_ln_w[l], w->mlp_ln_w[l], 4 * H));
+    LLB_CUDA_OK(cp(G.mlp_ln_b[l], w->mlp_ln_b[l], 4 * H));
+    LLB_CUDA_OK(cp(G.mlp4_b[l], w->mlp4_b[l], H));
+    LLB_CUDA_OK(cp(G.bond_emb[l], w->bond_emb[l], (size_t)BOND_VOCAB * H));
+    if (!G.predictor) {
+      LLB_CHECK_ARG(w->norm_w && w->norm_b, "gin: the encoder needs norms.{l}.weight/bias");
+      LLB_CUDA_OK(cp(G.norm_w[l], w->norm_w[l], H));
+      LLB_CUDA_OK(cp(G.norm_b[l], w->norm_b[l], H));
+    }
+    if (l < G.L - 1) {
+      LLB_TRY(launch_f32_to_bf16(w->vn0_w[l], H, bf(G.vn0_w[l]), H, 4 * H, H, H, s));
+      LLB_TRY(launch_f32_to_bf16(w->vn4_w[l], 4 * H, bf(G.vn4_w[l]), 4 * H, H, 4 * H, 4 * H, s));
+      LLB_CUDA_OK(cp(G.vn0_b[l], w->vn0_b[l], 4 * H));
+      LLB_CUDA_OK(cp(G.vn_ln_w[l], w->vn_ln_w[l], 4 * H));
+      LLB_CUDA_OK(cp(G.vn_ln_b[l], w->vn_ln_b[l], 4 * H));
+      LLB_CUDA_OK(cp(G.vn4_b[l], w->vn4_b[l], H));
+    }
+    if (G.predictor) {
+      LLB_TRY(launch_f32_to_bf16(w->adapter_w[l], G.tdim, bf(G.adapter_w[l]), G.tdim, 3 * H, G.tdim, G.tdim, s));
+      LLB_CUDA_OK(cp(G.adapter_b[l], w->adapter_b[l], 3 * H));
+    }
+  }
+  if (G.predictor) LLB_CUDA_OK(cp(G.text_drop, w->text_dropping, G.tdim));
+  LLB_TRY(launch_f32_to_bf16(w->head0_w, H, bf(G.head0_w), H, G.HH, H, H, s));
+  LLB_TRY(launch_f32_to_bf16(w->head4_w, G.HH, bf(G.head4_w), G.HH, G.HO, G.HH, G.HH, s));
+  LLB_CUDA_OK(cp(G.head0_b, w->head0_b, G.HH));
+  LLB_CUDA_OK(cp(G.head_ln_w, w->head_ln_w, G.HH));
+  LLB_CUDA_OK(cp(G.head_ln_b, w->head_ln_b, G.HH));
+  LLB_CUDA_OK(cp(G.head4_b, w->head4_b, G.HO));
+  return LLB_OK;
+}
+
+int llb_gin_create(const llb_gin_config* cfg, const void* packed, size_t packed_bytes, llb_gin** out) {
+  LLB_TRY(require_sm100());
+  LLB_CHECK_ARG(cfg && packed && out, "llb_gin_create: null argument");
+  llb_gin* g = new llb_gin();
+  g->cfg = *cfg;
+  int st = make_layout(*cfg, g->G);
+  if (st == LLB_OK && packed_bytes < g->G.total)
+    st = fail(LLB_ERR_WORKSPACE, "gin: packed blob needs %zu bytes, got %zu", g->G.total, packed_bytes);
+  if (st != LLB_OK) {
+    delete g;
+    return st;
+  }
+  g->blob = (const uint8_t*)packed;
+  *out = g;
+  return LLB_OK;
+}
+
+void llb_gin_destroy(llb_gin* g) { delete g; }
+
+int llb_gin_workspace_bytes(const llb_gin_config* cfg, int num_nodes, int num_edges, int num_graphs, int want_logits,
+                            size_t* bytes) {
+  LLB_CHECK_ARG(cfg && bytes && num_nodes >= 1 && num_edges >= 0 && num_graphs >= 1, "llb_gin_workspace_bytes: bad argument");
+  llb_gin tmp;
+  tmp.cfg = *cfg;
+  LLB_TRY(make_layout(*cfg, tmp.G));
+  return gin_carve(&tmp, nullptr, 0, num_nodes, num_edges, num_graphs, want_logits != 0, bytes);
+}
+
+int llb_gin_bind(llb_gin* g, void* workspace, size_t workspace_bytes, int num_nodes, int num_edges, int num_graphs,
+                 const int64_t* x, const int64_t* edge_index, const int64_t* edge_attr, const int64_t* batch,
+                 llb_stream_t stream) {
+  LLB_CHECK_ARG(g && workspace && x && batch && num_nodes >= 1 && num_graphs >= 1 && num_edges >= 0, "llb_gin_bind: bad argument");
+  LLB_CHECK_ARG(num_edges == 0 || (edge_index && edge_attr), "llb_gin_bind: null edge arrays");
+  LLB_CHECK_ARG(num_edges < (1 << 28), "llb_gin_bind: too many edges");
+  cudaStream_t s = (cudaStream_t)stream;
+  size_t need = 0;
+  // logits scratch is carved whenever the workspace is large enough for it (top-k path); forward() writes to the caller's buffer
+  LLB_TRY(gin_carve(g, workspace, workspace_bytes, num_nodes, num_edges, num_graphs, true, &need));
+  g->want_logits = need <= workspace_bytes;
+  if (!g->want_logits) {
+    LLB_TRY(gin_carve(g, workspace, workspace_bytes, num_nodes, num_edges, num_graphs, false, &need));
+    g->logits_ws = nullptr;
+    if (need > workspace_bytes) return fail(LLB_ERR_WORKSPACE, "gin: workspace needs %zu bytes, got %zu", need, workspace_bytes);
+  }
+  g->n = num_nodes, g->e = num_edges, g->B = num_graphs;
+  const int n = num_nodes, e = num_edges;
+  gin_prep_nodes_kernel<<<ceil_div(n, 256), 256, 0, s>>>(x, batch, g->x32, g->batch32, g->graph_ptr, n, num_graphs);
+  LLB_CUDA_OK(cudaGetLastError());
+  LLB_CUDA_OK(cudaMemsetAsync(g->deg, 0, (size_t)(n + 1) * 4, s));
+  if (e > 0) {
+    gin_degree_kernel<<<ceil_div(e, 256), 256, 0, s>>>(edge_index, g->deg, e, n);
+    LLB_CUDA_OK(cudaGetLastError());
+  }
+  LLB_TRY(gin_scan(g, s));
+  LLB_CUDA_OK(cudaMemsetAsync(g->deg, 0, (size_t)(n + 1) * 4, s));
+  if (e > 0) {
+    gin_fill_kernel<<<ceil_div(e, 256), 256, 0, s>>>(edge_index, edge_attr, g->rowptr, g->deg, g->col, g->eid, e, n);
+    gin_sort_rows_kernel<<<ceil_div(n, 256), 256, 0, s>>>(g->rowptr, g->col, g->eid, n);
+    LLB_CUDA_OK(cudaGetLastError());
+  }
+  g->launches += 4;
+  return LLB_OK;
+}
+
+int llb_gin_encoder_forward(llb_gin* g, float* out, float* pooled_or_null, llb_stream_t stream) {
+  LLB_CHECK_ARG(g && out && !g->G.predictor, "llb_gin_encoder_forward: needs an encoder handle and an output buffer");
+  cudaStream_t s = (cudaStream_t)stream;
+  const GinLayout& G = g->G;
+  LLB_TRY(gin_trunk(g, nullptr, s));
+  if (pooled_or_null) LLB_CUDA_OK(cudaMemcpyAsync(pooled_or_null, g->pooled, (size_t)g->B * G.H * 4, cudaMemcpyDeviceToDevice, s));
+  LLB_TRY(gin_mlp4(g, g->pooled_b, g->B, G.head0_w, G.head0_b, G.head_ln_w, G.head_ln_b, G.head4_w, G.head4_b, G.HH, G.HO, g->hz,
+                   g->head_out, G.H, s));
+  RowLnArgs a;
+  a.in = g->head_out, a.in_ld = G.H, a.rows = g->B, a.width = G.H, a.normalize = false, a.l2_normalize = true;
+  a.out_f32 = out, a.out_f32_ld = G.H;
+  LLB_TRY(launch_row_ln(a, s));
+  g->launches++;
+  return LLB_OK;
+}
+
+static int gin_head_hidden(llb_gin* g, cudaStream_t s) {
+  // decoder.0 -> LayerNorm -> GELU, result (B,4H) bf16 in g->hz
+  const GinLayout& G = g->G;
+  LLB_TRY(gemm_bias_act(g->pooled_b, G.H, g->w<void>(G.head0_w), G.H, g->w<float>(G.head0_b), g->hz, G.HH, g->B, G.HH, G.H,
+                        LLB_ACT_NONE, false, s, &g->ctr));
+  RowLnArgs a;
+  a.in = g->hz, a.in_ld = G.HH, a.in_bf16 = true, a.rows = g->B, a.width = G.HH;
+  a.gamma = g->w<float>(G.head_ln_w), a.beta = g->w<float>(G.head_ln_b), a.act = LLB_ACT_GELU;
+  a.out_bf16 = g->hz, a.out_bf16_ld = G.HH;
+  LLB_TRY(launch_row_ln(a, s));
+  g->launches++;
+  return LLB_OK;
+}
+
+int llb_gin_predictor_forward(llb_gin* g, const float* c, float* logits, llb_stream_t stream) {
+  LLB_CHECK_ARG(g && logits && g->G.predictor, "llb_gin_predictor_forward: needs a predictor handle and an output buffer");
+  cudaStream_t s = (cudaStream_t)stream;
+  const GinLayout& G = g->G;
+  LLB_TRY(gin_trunk(g, c, s));
+  LLB_TRY(gin_head_hidden(g, s));
+  return gemm_bias_act(g->hz, G.HH, g->w<void>(G.head4_w), G.HH, g->w<float>(G.head4_b), logits, G.out_dim, g->B, G.out_dim, G.HH,
+                       LLB_ACT_NONE, true, s, &g->ctr);
+}
+
+int llb_gin_predictor_topk(llb_gin* g, const float* c, int k, float* topk_prob, int32_t* topk_idx, llb_stream_t stream) {
+  LLB_CHECK_ARG(g && topk_prob && topk_idx && g->G.predictor, "llb_gin_predictor_topk: needs a predictor handle and output buffers");
+  const GinLayout& G = g->G;
+  LLB_CHECK_ARG(k >= 1 && k <= G.out_dim, "llb_gin_predictor_topk: k=%d outside [1,%d]", k, G.out_dim);
+  if (!g->logits_ws) return fail(LLB_ERR_WORKSPACE, "llb_gin_predictor_topk: bind the batch with a workspace sized with want_logits=1");
+  cudaStream_t s = (cudaStream_t)stream;
+  LLB_TRY(gin_trunk(g, c, s));
+  LLB_TRY(gin_head_hidden(g, s));
+  for (int r0 = 0; r0 < g->B; r0 += g->chunk_rows) {
+    const int rows = g->B - r0 < g->chunk_rows ? g->B - r0 : g->chunk_rows;
+    LLB_TRY(gemm_bias_act(g->hz + (size_t)r0 * G.HH, G.HH, g->w<void>(G.head4_w), G.HH, g->w<float>(G.head4_b), g->logits_ws, G.out_dim,
+                          rows, G.out_dim, G.HH, LLB_ACT_NONE, true, s, &g->ctr));
+    gin_topk_kernel<<<rows, 1024, 0, s>>>(g->logits_ws, G.out_dim, G.out_dim, k, topk_prob + (size_t)r0 * k, topk_idx + (size_t)r0 * k);
+    LLB_CUDA_OK(cudaGetLastError());
+    g->launches++;
+  }
+  return LLB_OK;
+}
+
+int64_t llb_gin_launch_count(const llb_gin* g) { return g ? g->launches + g->ctr.launches : 0; }
+
+int llb_cost_mlp(const float* w0, const float* b0, const float* w1, const float* b1, const float* fps, int n, int fp_dim,
+                 int latent, float* out, llb_stream_t stream) {
+  LLB_TRY(require_sm100());
+  LLB_CHECK_ARG(w0 && b0 && w1 && b1 && fps && out && n >= 1 && fp_dim >= 1 && latent >= 1 && latent <= 4096, "llb_cost_mlp: bad argument");
+  cost_mlp_kernel<<<n, 256, latent * sizeof(float), (cudaStream_t)stream>>>(w0, b0, w1, b1, fps, fp_dim, latent, out);
+  LLB_CUDA_OK(cudaGetLastError());
+  return LLB_OK;
+}
+
+}  // extern "C"

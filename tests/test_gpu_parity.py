@@ -1,0 +1,282 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against the golden
+fixtures produced by the unmodified reference (tests/golden) and against the CPU oracle on seeded inputs.
+
+Stated tolerances (bf16 tensor-core operands, fp32 accumulation and fp32 LayerNorm/softmax/posterior, measured
+against the reference at model_dtype=float32):
+  denoiser logits   : rms <= 0.02, max |d| <= 0.10          (the reference's own bf16 mode: rms 0.024, max 0.143)
+  posterior probs   : |d| <= 2e-5 given identical logits; sampled categories bit-exact given identical logits+noise
+  sampled categories: bit-exact wherever the oracle's decision margin log(top1/top2 of p/q) > 0.35
+  GIN embeddings    : max |d| <= 1e-3 on unit-norm rows;  predictor logits: max |d| <= 0.03, rms <= 0.006
+"""
+import math
+import os
+import tempfile
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from llamole_b200 import GraphCLIP, GraphDiT, GraphPredictor, _cabi, synth  # noqa: E402
+from llamole_b200.graph_decoder import state_from_onehot  # noqa: E402
+
+DEV = "cuda:0"
+
+
+def _stats(a, b):
+    d = (a.double() - b.double()).abs()
+    return float(d.max()), float(d.pow(2).mean().sqrt())
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("M,N,K", [(1, 64, 64), (50, 266, 1024), (128, 256, 64), (200, 1024, 320), (1000, 3072, 1024),
+                                   (333, 192, 4096), (4097, 768, 768), (129, 6144, 1024)])
+@pytest.mark.parametrize("act,out_f32", [(0, 1), (1, 0), (2, 1), (3, 0)])
+def test_gemm_matches_torch(M, N, K, act, out_f32):
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
+    A = (torch.randn(M, K, generator=g) * 0.5).to(DEV).bfloat16()
+    W = (torch.randn(N, K, generator=g) * (1.0 / math.sqrt(K))).to(DEV).bfloat16()
+    bias = torch.randn(N, generator=g).to(DEV)
+    C = torch.full((M, N), float("nan"), device=DEV, dtype=torch.float32 if out_f32 else torch.bfloat16)
+    lib = _cabi.lib()
+    _cabi.check(lib.llb_gemm_bf16(_cabi.ptr(A), K, _cabi.ptr(W), K, _cabi.ptr(bias), _cabi.ptr(C), N, M, N, K, act, out_f32,
+                                  _cabi.stream_ptr()), "llb_gemm_bf16")
+    torch.cuda.synchronize()
+    ref = A.float() @ W.float().t() + bias
+    ref = [ref, torch.nn.functional.gelu(ref), torch.nn.functional.silu(ref), ref / (1 + ref.abs())][act]
+    mx, rms = _stats(C.float(), ref)
+    tol = 2e-4 if out_f32 else 2e-2
+    assert not torch.isnan(C.float()).any()
+    assert mx < tol * max(1.0, float(ref.abs().max())), (mx, rms)
+
+
+# ------------------------------------------------------------------------------------------------ GraphDiT
+@pytest.fixture(scope="module")
+def dit(dit_small):
+    fx = dit_small
+    P = fx["params"]
+    d = tempfile.mkdtemp()
+    sd = synth.dit_state_dict(fx["cfg"], P["max_nodes"], P["w_seed"])
+    synth.write_dit_checkpoint(d, fx["cfg"], fx["meta"], sd)
+    m = GraphDiT(os.path.join(d, "config.yaml"), os.path.join(d, "data.meta.json"), torch.float32)
+    m.init_model(d)
+    m.disable_grads()
+    return m.to(DEV)
+
+
+def _bind(m, fx):
+    eng = m.engine()
+    props = torch.where(fx["props"] == -200.0, float("nan"), fx["props"]).to(DEV).contiguous()
+    eng.begin(fx["n_nodes"].to(torch.int32), props, fx["txt"].to(DEV).contiguous())
+    return eng
+
+
+def test_dit_tables_and_initial_state(dit, dit_small):
+    m, fx = dit, dit_small
+    eng = _bind(m, fx)
+    assert torch.equal(m.betas, fx["schedule_betas"]) and torch.equal(m.alphas_bar, fx["schedule_abar"])
+    assert torch.equal(m.x_marginals, fx["x_marg"]) and torch.equal(m.xe_conditions, fx["xe"]) and torch.equal(m.ex_conditions, fx["ex"])
+    eng.init_state(0, fx["qX0"].to(DEV), fx["qE0"].to(DEV))
+    X, E = eng.get_state()
+    Xr, Er = state_from_onehot(fx["X_T"], fx["E_T"])
+    assert torch.equal(X.cpu(), Xr) and torch.equal(E.cpu(), Er)
+
+
+def _mask(fx):
+    N = fx["params"]["max_nodes"]
+    return torch.arange(N).unsqueeze(0) < fx["n_nodes"].unsqueeze(1)
+
+
+def _state_at(fx, i):
+    """State consumed by loop iteration i (i = 0 -> z_T)."""
+    if i == 0:
+        return state_from_onehot(fx["X_T"], fx["E_T"])
+    mask = _mask(fx)
+    X = fx["cat_X"][i - 1].clone()
+    E = fx["cat_E"][i - 1].clone()
+    X[~mask] = -1
+    E[~(mask.unsqueeze(1) & mask.unsqueeze(2))] = -1
+    return X, E
+
+
+def test_dit_denoiser_logits(dit, dit_small):
+    m, fx = dit, dit_small
+    eng = _bind(m, fx)
+    T = fx["cfg"]["diffusion_steps"]
+    worst = (0.0, 0.0)
+    for i in (0, 1, 5, T - 1):
+        eng.set_state(*_state_at(fx, i))
+        for unc, kx, ke in ((False, "logits_cond_X", "logits_cond_E"), (True, "logits_unc_X", "logits_unc_E")):
+            lX, lE = eng.denoise(T - i, unc)
+            torch.cuda.synchronize()
+            mx, rms = _stats(torch.cat([lX.cpu().flatten(), lE.cpu().flatten()]), torch.cat([fx[kx][i].flatten(), fx[ke][i].flatten()]))
+            worst = (max(worst[0], mx), max(worst[1], rms))
+            # structure: symmetric E, zero diagonal / masked entries exactly
+            assert torch.equal(lE, lE.transpose(1, 2))
+            assert float((lE.cpu() * (fx[ke][i] == 0)).abs().max()) == 0.0
+    print(f"\n[parity] denoiser logits vs fp32 reference: max|d|={worst[0]:.4f} rms={worst[1]:.5f} (logit std {float(fx['logits_cond_X'].std()):.2f})")
+    assert worst[0] <= 0.10 and worst[1] <= 0.02, worst
+
+
+def _margins(prob, q, valid):
+    s = prob.clamp_min(1e-5) / q
+    top2 = s.topk(2, dim=-1).values
+    return torch.log(top2[..., 0] / top2[..., 1])[valid]
+
+
+def test_dit_posterior_and_sampling_bit_exact_given_logits(dit, dit_small):
+    m, fx = dit, dit_small
+    eng = _bind(m, fx)
+    T = fx["cfg"]["diffusion_steps"]
+    mask = _mask(fx)
+    pair = mask.unsqueeze(1) & mask.unsqueeze(2) & torch.triu(torch.ones(mask.shape[1], mask.shape[1], dtype=torch.bool), 1)
+    for i in range(T):
+        t = T - i
+        eng.set_state(*_state_at(fx, i))
+        pX, pE = eng.posterior_sample(t, fx["logits_cond_X"][i].to(DEV), fx["logits_cond_E"][i].to(DEV), fx["logits_unc_X"][i].to(DEV),
+                                      fx["logits_unc_E"][i].to(DEV), 0, fx["qX"][t - 1].to(DEV), fx["qE"][t - 1].to(DEV))
+        X, E = eng.get_state()
+        torch.cuda.synchronize()
+        assert float((pX.cpu() - fx["prob_X"][i])[mask].abs().max()) <= 2e-5
+        assert float((pE.cpu() - fx["prob_E"][i])[pair].abs().max()) <= 2e-5
+        Xr, Er = _state_at(fx, i + 1) if i + 1 < T else (None, None)
+        if Xr is None:
+            Xr = fx["final_X"]
+            Er = fx["final_E"].clone()
+            idx = torch.arange(mask.shape[1])
+            Er[:, idx, idx] = torch.where(mask, torch.zeros_like(Er[:, idx, idx]), Er[:, idx, idx])
+        # tiny-margin decisions may flip on a 1-ulp difference of the closed form; everything else must be bit-exact
+        mx = _margins(fx["prob_X"][i], fx["qX"][t - 1], mask)
+        me = _margins(fx["prob_E"][i], fx["qE"][t - 1], pair)
+        okx = (X.cpu() == Xr)[mask] | (mx < 1e-3)
+        oke = (E.cpu() == Er)[pair] | (me < 1e-3)
+        assert bool(okx.all()) and bool(oke.all())
+        assert torch.equal(E, E.transpose(1, 2))
+        inval = ~(mask.unsqueeze(1) & mask.unsqueeze(2))
+        assert bool((E.cpu()[inval] == -1).all()) and bool((X.cpu()[~mask] == -1).all())
+
+
+def test_dit_reverse_steps_teacher_forced(dit, dit_small):
+    """Full step (denoiser + posterior + sampling) from the oracle's state at every step: categories must agree
+    wherever the oracle's decision margin exceeds the stated tolerance."""
+    m, fx = dit, dit_small
+    eng = _bind(m, fx)
+    T = fx["cfg"]["diffusion_steps"]
+    mask = _mask(fx)
+    N = mask.shape[1]
+    pair = mask.unsqueeze(1) & mask.unsqueeze(2) & torch.triu(torch.ones(N, N, dtype=torch.bool), 1)
+    agree = total = 0
+    for i in range(T):
+        t = T - i
+        eng.set_state(*_state_at(fx, i))
+        pX, pE = eng.step(t, 0, fx["qX"][t - 1].to(DEV), fx["qE"][t - 1].to(DEV), want_probs=True)
+        X, E = eng.get_state()
+        torch.cuda.synchronize()
+        Xr, Er = fx["cat_X"][i], fx["cat_E"][i]
+        mx = _margins(fx["prob_X"][i], fx["qX"][t - 1], mask)
+        me = _margins(fx["prob_E"][i], fx["qE"][t - 1], pair)
+        eqx, eqe = (X.cpu() == Xr)[mask], (E.cpu() == Er)[pair]
+        assert bool((eqx | (mx < 0.35)).all()), f"step t={t}: atom category differs at margin {float(mx[~eqx].max()):.3f}"
+        assert bool((eqe | (me < 0.35)).all()), f"step t={t}: bond category differs at margin {float(me[~eqe].max()):.3f}"
+        agree += int(eqx.sum()) + int(eqe.sum())
+        total += eqx.numel() + eqe.numel()
+        assert float((pX.cpu() - fx["prob_X"][i])[mask].abs().max()) < 0.08
+    print(f"\n[parity] teacher-forced category agreement: {agree}/{total} = {agree / total:.4f}")
+    assert agree / total > 0.97
+
+
+def test_dit_generate_graphs_end_to_end(dit, dit_small):
+    m, fx = dit, dit_small
+    eng = _bind(m, fx)
+    noise = {k: fx[k] for k in ("qX0", "qE0", "qX", "qE")}
+    X, E, n = m.generate_graphs(fx["props"], fx["txt"], -200, n_nodes=fx["n_nodes"], noise=noise)
+    torch.cuda.synchronize()
+    mask = _mask(fx)
+    assert bool((X.cpu()[~mask] == -1).all()) and bool((X.cpu()[mask] >= 0).all())
+    assert torch.equal(E, E.transpose(1, 2))
+    same = float((X.cpu() == fx["final_X"].long())[mask].float().mean())
+    print(f"\n[parity] free-running {fx['cfg']['diffusion_steps']}-step trajectory: final atom agreement {same:.3f}")
+    # counter-RNG path: deterministic and independent of batch composition (keyed by global molecule index)
+    Xa, Ea, _ = m.generate_graphs(fx["props"], fx["txt"], -200, n_nodes=fx["n_nodes"], seed=11)
+    Xb, Eb, _ = m.generate_graphs(fx["props"][2:], fx["txt"][2:], -200, n_nodes=fx["n_nodes"][2:], seed=11, mol_index_base=2)
+    assert torch.equal(Xa[2:], Xb) and torch.equal(Ea[2:], Eb)
+
+
+def test_dit_counter_rng_matches_host_restatement(dit, dit_small):
+    import numpy as np
+
+    from oracle import llamole_oracle as O
+
+    m, fx = dit, dit_small
+    eng = _bind(m, fx)
+    N = fx["params"]["max_nodes"]
+    T = fx["cfg"]["diffusion_steps"]
+    seed = 0x1234567811
+    eng.init_state(seed, None, None)
+    X, E = eng.get_state()
+    torch.cuda.synchronize()
+    tb = O.dit_tables(fx["meta"])
+    B = fx["n_nodes"].numel()
+    mol = np.arange(B)[:, None]
+    qx = O.counter_noise(seed, T, mol, np.arange(N)[None, :], 16)
+    Xh = (tb.x_marg.numpy()[None, None, :] / qx).argmax(-1)
+    mask = _mask(fx)
+    assert torch.equal(X.cpu()[mask].long(), torch.from_numpy(Xh)[mask])
+    ii, jj = np.meshgrid(np.arange(N), np.arange(N), indexing="ij")
+    qe = O.counter_noise(seed, T, np.arange(B)[:, None, None], (N + ii * N + jj)[None], 5)
+    Eh = torch.from_numpy((tb.e_marg.numpy()[None, None, None, :] / qe).argmax(-1))
+    pair = mask.unsqueeze(1) & mask.unsqueeze(2) & torch.triu(torch.ones(N, N, dtype=torch.bool), 1)
+    assert torch.equal(E.cpu()[pair].long(), Eh[pair])
+
+
+# ------------------------------------------------------------------------------------------------ GIN
+def test_gin_encoder_matches_reference(gin_small):
+    fx = gin_small
+    P = fx["params"]
+    d = tempfile.mkdtemp()
+    synth.write_encoder_checkpoint(d, P["L"], P["H"], P["enc_seed"])
+    g = GraphCLIP(P["L"], P["H"], 0.0, {})
+    g.init_model(d, verbose=False)
+    g = g.to(DEV)
+    eng = g.engine()
+    eng.bind(fx["x"], fx["edge_index"], fx["edge_attr"], fx["batch"])
+    emb, pooled = eng.encoder_forward(want_pooled=True)
+    torch.cuda.synchronize()
+    mx_p, rms_p = _stats(pooled.cpu(), fx["encoder_pooled"])
+    mx, rms = _stats(emb.cpu(), fx["encoder_embedding"])
+    print(f"\n[parity] GIN encoder: pooled max|d|={mx_p:.4f} (std {float(fx['encoder_pooled'].std()):.2f}); embedding max|d|={mx:.2e} rms={rms:.2e}")
+    assert mx <= 1e-3 * math.sqrt(768 / P["H"]) * 3  # unit-norm rows: entries scale with 1/sqrt(H)
+    out = g(fx["x"], fx["edge_index"], fx["edge_attr"], fx["batch"])
+    assert out.shape == fx["encoder_embedding"].shape and torch.allclose(out.norm(dim=-1).cpu(), torch.ones(out.shape[0]), atol=1e-4)
+    # edge order must not matter (CSR build sorts by destination)
+    perm = torch.randperm(fx["edge_attr"].numel(), generator=torch.Generator().manual_seed(0))
+    out2 = g(fx["x"], fx["edge_index"][:, perm], fx["edge_attr"][perm], fx["batch"])
+    assert float((out2 - out).abs().max()) < 2e-3
+
+
+def test_gin_predictor_matches_reference(gin_small):
+    fx = gin_small
+    P = fx["params"]
+    d = tempfile.mkdtemp()
+    synth.write_predictor_checkpoint(d, P["L"], P["H"], P["out_dim"], P["pred_seed"])
+    gp = GraphPredictor(P["L"], P["H"], 0.0, P["out_dim"], {}, {i: f"T{i}" for i in range(P["out_dim"])})
+    gp.init_model(d)
+    gp.init_neural_cost(d)
+    gp = gp.to(DEV)
+    g = (fx["x"], fx["edge_index"], fx["edge_attr"], fx["batch"])
+    lc = gp(*g, fx["c"].to(DEV))
+    ln = gp(*g, None)
+    torch.cuda.synchronize()
+    for got, key in ((lc, "predictor_logits"), (ln, "predictor_logits_dropped")):
+        mx, rms = _stats(got.cpu(), fx[key])
+        print(f"\n[parity] GIN predictor {key}: max|d|={mx:.4f} rms={rms:.5f} (std {float(fx[key].std()):.2f})")
+        assert mx <= 0.03 and rms <= 0.006, (mx, rms)
+    probs, idx = gp.topk_templates(*g, fx["c"].to(DEV), 10)
+    torch.cuda.synchronize()
+    ref_p = torch.softmax(lc.float().cpu(), dim=1)
+    tv, ti = torch.topk(ref_p, 10, dim=1)
+    assert torch.equal(idx.cpu().long(), ti) and torch.allclose(probs.cpu(), tv, atol=1e-5)
+    overlap = sum(len(set(a.tolist()) & set(b.tolist())) for a, b in zip(idx.cpu(), fx["topk_indices"])) / idx.numel()
+    assert overlap >= 0.9
+    cost = gp.cost_from_fingerprints(fx["fps"])
+    assert torch.allclose(cost.cpu(), fx["cost"], atol=1e-5)
