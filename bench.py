@@ -1,0 +1,425 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: GraphDiT molecules/s (500-step sampling) and GIN graphs/s on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One JSON line on rank 0 (contract in the task statement / DESIGN.md section "Measurement"):
+  * headline `value`  = GraphDiT molecules/s, whole job over all N GPUs, BASELINE.json configs[2]
+    (multi-conditional 500-step reverse diffusion, batch 2048 per GPU, checkpoint shape H=1024 / depth 28 /
+    heads 16 / 50 nodes / guide scale 2, random-init weights, synthetic conditions, every molecule at the full
+    50 atoms).  A "step" is ONE reverse-diffusion step over the whole batch (conditional + unconditional denoiser
+    pass, posterior, guidance, sampling); molecules/s = batch / (T * seconds per step).
+  * `gin` sub-object = GraphCLIP encoder graphs/s over 4096 synthetic molecular graphs per GPU (configs[1]).
+  * `e2e`            = the same metric through the public drop-in API with host buffers (H2D + D2H inside the
+                       timed region).
+  * `roofline`       = dominant kernel (live CUDA-event timing inside the timed region) against the measured peak.
+  * `cpu_baseline`   = the CPU oracle (the reference's algorithm in PyTorch fp32) on the box's host cores.
+`--impl reference` times that CPU implementation alone with the same metric/config keys.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "GraphDiT molecules/sec (500-step sampling) and GIN graphs/sec at 1/2/4/8 B200"
+DIT = dict(hidden=1024, depth=28, heads=16, mlp_ratio=4.0, T=500, guide_scale=2.0, max_nodes=50)
+GIN = dict(hidden=768, layers=5)
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+def dit_flops_per_pass(n_nodes, H=1024, D=28, d0=266):
+    """Algorithmic FLOPs of one denoiser pass over molecules with n valid atoms each."""
+    n = n_nodes.double()
+    per = D * (n * 24 * H * H + 4 * n * n * H + 14 * H * H) + n * (2 * d0 * H + 2 * H * H + 2 * d0 * H) + 2 * (256 * H + H * H) + 2 * (H * H + 2 * d0 * H)
+    return float(per.sum())
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(self.rows[0][1]), "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# model construction (synthetic weights of the checkpoint's shapes; no files except two tiny configs)
+# ------------------------------------------------------------------------------------------------------
+def build_dit(device, small=False):
+    import yaml
+
+    from llamole_b200 import GraphDiT, synth
+
+    c = dict(DIT)
+    if small:
+        c.update(hidden=256, depth=2, heads=4)
+    cfg = synth.dit_config(c["hidden"], c["depth"], c["heads"], c["mlp_ratio"], c["T"], c["guide_scale"])
+    meta = synth.dit_meta(c["max_nodes"])
+    d = tempfile.mkdtemp(prefix="llb_bench_")
+    with open(os.path.join(d, "config.yaml"), "w") as f:
+        yaml.safe_dump(cfg, f)
+    with open(os.path.join(d, "data.meta.json"), "w") as f:
+        json.dump(meta, f)
+    m = GraphDiT(os.path.join(d, "config.yaml"), os.path.join(d, "data.meta.json"), torch.float32)
+    sd = synth.dit_state_dict(cfg, c["max_nodes"], seed=1234)
+    m.denoiser.load_state_dict(sd)
+    m.disable_grads()
+    return m.to(device), cfg, meta, sd
+
+
+def build_gin(device):
+    from llamole_b200 import GraphCLIP, synth
+
+    enc, proj = synth.gin_encoder_state_dicts(GIN["layers"], GIN["hidden"], seed=11)
+    g = GraphCLIP(GIN["layers"], GIN["hidden"], 0.0, {})
+    g.molecule_encoder.load_state_dict(enc)
+    g.molecule_projection.load_state_dict(proj)
+    g.disable_grads()
+    return g.to(device), enc, proj
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm on the host cores (oracle port; the verbatim reference when present)
+# ------------------------------------------------------------------------------------------------------
+def cpu_dit_step_seconds(cfg, meta, sd, B, steps, warmup):
+    from llamole_b200 import synth
+    from oracle import llamole_oracle as O
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    tb = O.dit_tables(meta)
+    U = O.union_transition(tb)
+    T = cfg["diffusion_steps"]
+    sched = O.cosine_schedule(T)
+    N = tb.max_nodes
+    props, txt = synth.dit_conditions(B)
+    y = torch.where(props == -200.0, torch.full_like(props, float("nan")), props)
+    node_mask = torch.ones(B, N, dtype=torch.bool)
+    g = torch.Generator().manual_seed(5)
+    ex = lambda *s: torch.empty(*s).exponential_(1.0, generator=g)  # noqa: E731
+    X, E = O.initial_state(tb, node_mask, ex(B, N, 16), ex(B, N, N, 5), torch.float32)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            X, E, _, _ = O.reverse_step(sd, cfg, tb, U, sched, X, E, node_mask, y, txt, T - i, ex(B, N, 16), ex(B, N, N, 5))
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    return sum(times) / len(times)
+
+
+def cpu_gin_seconds(enc, proj, graphs, reps=1):
+    from oracle import llamole_oracle as O
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            O.gin_encoder_forward(enc, proj, GIN["layers"], *graphs)
+        return (time.perf_counter() - t0) / reps
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU implementation of the path, same metric/config keys, rank 0 only."""
+    if rank != 0:
+        return
+    from llamole_b200 import synth
+
+    cfg = synth.dit_config(DIT["hidden"], DIT["depth"], DIT["heads"], DIT["mlp_ratio"], DIT["T"], DIT["guide_scale"])
+    meta = synth.dit_meta(DIT["max_nodes"])
+    sd = synth.dit_state_dict(cfg, DIT["max_nodes"], seed=1234)
+    B = 16
+    sec = cpu_dit_step_seconds(cfg, meta, sd, B, max(1, args.steps), max(0, args.warmup))
+    val = B / (DIT["T"] * sec)
+    enc, proj = synth.gin_encoder_state_dicts(GIN["layers"], GIN["hidden"], seed=11)
+    graphs = synth.molecular_graphs(512, seed=0)
+    gsec = cpu_gin_seconds(enc, proj, graphs)
+    cores = torch.get_num_threads()
+    sample = f"{B} of {args.dit_batch} molecules per step (one reverse step = cond+uncond denoiser pass + posterior + sampling), fp32, {cores} threads"
+    out = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "molecules/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": val, "unit": "molecules/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "molecules/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gin": {"value": 512 / gsec, "unit": "graphs/s", "sample": "512 of 4096 graphs, one encoder forward", "cores": cores},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(args):
+    return {
+        "workload": "BASELINE.json configs[2]: GraphDiT multi-conditional (7 of 10 properties + text embedding) 500-step reverse "
+                    "diffusion with classifier-free guidance, batch %d per GPU, all molecules at 50 atoms; a step = one reverse step "
+                    "over the batch" % args.dit_batch,
+        "dit": {"hidden": DIT["hidden"], "depth": DIT["depth"], "heads": DIT["heads"], "max_nodes": DIT["max_nodes"],
+                "timesteps": DIT["T"], "guide_scale": DIT["guide_scale"], "batch_per_gpu": args.dit_batch, "weights": "random-init"},
+        "gin_workload": "BASELINE.json configs[1]: GraphCLIP (GIN, H=768, L=5) forward over %d synthetic molecular graphs per GPU" % args.gin_graphs,
+        "l2": "activations per step (~7 GB) and GIN node matrices (~375 MB) exceed the 126 MB L2; no explicit flush",
+        "parallelism": "dp%d (independent molecule/graph shards, one NCCL all-gather of results)" % args.gpus,
+    }
+
+
+# ------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--dit-batch", type=int, default=2048)
+    ap.add_argument("--gin-graphs", type=int, default=4096)
+    ap.add_argument("--small", action="store_true", help="tiny model (debug only; invalid as a benchmark)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+    args.warmup = max(3, args.warmup)
+    args.steps = max(1, args.steps)
+
+    import torch.distributed as dist
+
+    from llamole_b200 import _cabi, synth
+
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    pk = peaks()
+    T = DIT["T"]
+    # ------------------------------------------------------------------ GraphDiT
+    m, cfg, meta, sd = build_dit(device, small=args.small)
+    eng = m.engine()
+    B = args.dit_batch
+    N = m.max_n_nodes
+    props_h, txt_h = synth.dit_conditions(B, seed=2024 + rank)
+    props_h, txt_h = props_h.pin_memory(), txt_h.pin_memory()
+    n_nodes = torch.full((B,), N, dtype=torch.int64)
+    props_d = props_h.to(device)
+    props_d = torch.where(props_d == -200.0, torch.full_like(props_d, float("nan")), props_d).contiguous()
+    eng.begin(n_nodes.to(torch.int32), props_d, txt_h.to(device).contiguous(), mol_index_base=rank * B)
+    eng.init_state(7, None, None)
+    for i in range(args.warmup):
+        eng.step(T - i, 7)
+    barrier()
+    launches0 = eng.launch_count()
+    _cabi.profile_enable(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        ev0.record()
+        for i in range(args.steps):
+            eng.step(T - ((args.warmup + i) % T), 7)
+        if world > 1:   # the path's one exchange: gather the sampled graphs (done once per sampling run)
+            Xs, Es = eng.get_state()
+            gx = [torch.empty_like(Xs) for _ in range(world)]
+            ge = [torch.empty_like(Es) for _ in range(world)]
+            dist.all_gather(gx, Xs)
+            dist.all_gather(ge, Es)
+        ev1.record()
+        barrier()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    prof = _cabi.profile_read()
+    _cabi.profile_enable(False)
+    dit_launches = eng.launch_count() - launches0
+    ms_step = ms_total / args.steps
+    value = world * B / (T * ms_step / 1e3)
+    flops_step = 2 * dit_flops_per_pass(n_nodes, cfg["hidden_size"], cfg["depth"], 16 + 5 * N)
+    step_frac = flops_step / (ms_step / 1e3) / (pk["tf_sustained"] * 1e12)
+    # dominant kernel by total live time
+    M_rows = 2 * int(n_nodes.sum())
+    H, F = cfg["hidden_size"], int(cfg["hidden_size"] * cfg["mlp_ratio"])
+    gemm_flops = {"gemm_qkv": 2.0 * M_rows * 3 * H * H, "gemm_proj": 2.0 * M_rows * H * H, "gemm_fc1": 2.0 * M_rows * F * H,
+                  "gemm_fc2": 2.0 * M_rows * H * F}
+    breakdown = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps} for k, v in prof.items()}
+    dom = max((k for k in prof if k in gemm_flops), key=lambda k: prof[k][0], default=None)
+    roofline = None
+    if dom:
+        dur = prof[dom][0] / prof[dom][1] / 1e3
+        ach = gemm_flops[dom] / dur / 1e12
+        roofline = {"bound": "tensor", "kernel": f"gemm_tcgen05_kernel ({dom})", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                    "frac": ach / pk["tf_sustained"], "traffic": None, "peak_source": pk["source"] + " (sustained: timed inside a long step)",
+                    "launch_ms": dur * 1e3, "flops_per_launch": gemm_flops[dom],
+                    "whole_step": {"flops_per_step": flops_step, "achieved": flops_step / (ms_step / 1e3) / 1e12, "frac": step_frac}}
+    # ------------------------------------------------------------------ e2e through the public API (host buffers)
+    k_e2e = min(args.steps, 10)
+    outX = torch.empty((B, N), dtype=torch.int64).pin_memory()
+    outE = torch.empty((B, N, N), dtype=torch.int64).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    X, E, _ = m.generate_graphs(props_h, txt_h, -200, n_nodes=n_nodes, seed=7, steps=k_e2e, mol_index_base=rank * B)
+    outX.copy_(X, non_blocking=True)
+    outE.copy_(E, non_blocking=True)
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    e2e_val = world * B / (T * (e2e_ms / k_e2e) / 1e3)
+    h2d = (props_h.numel() + txt_h.numel()) * 4 + B * 4
+    d2h = (outX.numel() + outE.numel()) * 8
+    e2e = {"value": e2e_val, "unit": "molecules/s", "h2d_bytes_per_step": h2d / k_e2e, "d2h_bytes_per_step": d2h / k_e2e,
+           "note": f"GraphDiT.generate_graphs(host tensors, steps={k_e2e}) + D2H of the integer graphs; one call's copies amortised over its {k_e2e} reverse steps"}
+    del X, E
+    # ------------------------------------------------------------------ GIN encoder
+    gin = bench_gin(args, device, rank, world, barrier, max_over_ranks, pk)
+    # ------------------------------------------------------------------ CPU baseline (rank 0, N=1)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.small:
+        t0 = time.time()
+        sec = cpu_dit_step_seconds(cfg, meta, sd, 16, 3, 1)
+        cores = torch.get_num_threads()
+        cpu = {"value": 16 / (T * sec), "unit": "molecules/s", "cores": cores, "kind": "port",
+               "sample": f"16 of {B} molecules, 3 reverse steps after 1 warm-up ({sec:.2f} s/step), scaled to T={T}; oracle/llamole_oracle.py in fp32"}
+        gin["cpu_baseline"] = gin_cpu_baseline(gin)
+        log(f"cpu baseline took {time.time() - t0:.1f}s")
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": "molecules/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic", "config": workload_config(args), "clocks": clocks.summary(), "e2e": e2e,
+            "gpu_launches": int(dit_launches + gin.pop("_launches")), "roofline": roofline, "cpu_baseline": cpu,
+            "kernel_breakdown": breakdown, "gin": gin,
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def gin_cpu_baseline(gin):
+    from llamole_b200 import synth
+
+    enc, proj = synth.gin_encoder_state_dicts(GIN["layers"], GIN["hidden"], seed=11)
+    graphs = synth.molecular_graphs(512, seed=0)
+    sec = cpu_gin_seconds(enc, proj, graphs)
+    return {"value": 512 / sec, "unit": "graphs/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "first 512 of the 4096 graphs, one GraphCLIP forward, oracle/llamole_oracle.py in fp32"}
+
+
+def bench_gin(args, device, rank, world, barrier, max_over_ranks, pk):
+    from llamole_b200 import _cabi, synth
+
+    g, enc, proj = build_gin(device)
+    G = args.gin_graphs
+    x, ei, ea, batch = synth.molecular_graphs(G, seed=rank)
+    xd, eid, ead, bd = (t.to(device) for t in (x, ei, ea, batch))
+    n, e = int(x.numel()), int(ea.numel())
+    eng = g.engine()
+    iters = max(10, args.steps)
+    for _ in range(max(3, args.warmup)):
+        eng.bind(xd, eid, ead, bd, num_graphs=G)
+        out = eng.encoder_forward()
+    barrier()
+    l0 = eng.launch_count()
+    _cabi.profile_enable(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(iters):
+        eng.bind(xd, eid, ead, bd, num_graphs=G)
+        out = eng.encoder_forward()
+    ev1.record()
+    barrier()
+    ms = max_over_ranks(ev0.elapsed_time(ev1)) / iters
+    prof = _cabi.profile_read()
+    _cabi.profile_enable(False)
+    launches = eng.launch_count() - l0
+    H, L = GIN["hidden"], GIN["layers"]
+    agg_bytes = (e + 2 * n) * H * 2      # per layer launch (gathered neighbours + self, bf16, + output)
+    agg_ms = prof["gin_aggregate"][0] / prof["gin_aggregate"][1]
+    mlp_flops = 16.0 * n * H * H * L + 16.0 * H * H * (L - 1) * G + 4.0 * H * H * G
+    gemm_ms = sum(prof[k][0] for k in ("gin_gemm_mlp0", "gin_gemm_mlp4") if k in prof) / iters
+    # e2e: host int64 tensors -> embeddings on the host
+    xp, eip, eap, bp = (t.pin_memory() for t in (x, ei, ea, batch))
+    host_out = torch.empty((G, H), dtype=torch.float32).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        emb = g(xp.to(device, non_blocking=True), eip.to(device, non_blocking=True), eap.to(device, non_blocking=True), bp.to(device, non_blocking=True))
+        host_out.copy_(emb, non_blocking=True)
+        torch.cuda.synchronize()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / reps)
+    return {
+        "value": world * G / (ms / 1e3), "unit": "graphs/s", "ms_per_forward": ms, "graphs_per_gpu": G, "nodes": n, "directed_edges": e,
+        "config": {"hidden": H, "layers": L, "timed": "CSR build (llb_gin_bind) + GraphCLIP forward, inputs resident in HBM"},
+        "e2e": {"value": world * G / (e2e_ms / 1e3), "unit": "graphs/s", "h2d_bytes_per_step": (n * 2 + e * 3) * 8, "d2h_bytes_per_step": G * H * 4},
+        "roofline": {"bound": "hbm", "kernel": "gin_aggregate_kernel", "achieved": agg_bytes / (agg_ms / 1e3) / 1e9, "peak": pk["hbm"],
+                     "unit": "GB/s", "frac": agg_bytes / (agg_ms / 1e3) / 1e9 / pk["hbm"], "traffic": None, "launch_ms": agg_ms,
+                     "bytes_per_launch": agg_bytes, "peak_source": pk["source"]},
+        "mlp_gemms": {"tflops": mlp_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms else None, "frac_of_sustained": mlp_flops / (gemm_ms / 1e3) / 1e12 / pk["tf_sustained"] if gemm_ms else None,
+                      "ms_per_forward": gemm_ms},
+        "kernel_breakdown": {k: {"ms_per_forward": v[0] / iters, "launches": v[1] / iters} for k, v in prof.items()},
+        "_launches": launches,
+    }
+
+
+if __name__ == "__main__":
+    main()

@@ -44,6 +44,21 @@ int llb_version(void);
 int llb_arch_check(int device);
 
 /* ------------------------------------------------------------------------------------------------------
+ * Live kernel timing (bench.py's roofline): when enabled, every kernel launch of the library is bracketed by
+ * CUDA events on the launching stream and accumulated per slot.  llb_profile_read synchronises on the recorded
+ * events, returns the slot's total device time and launch count since the last reset, and clears it.
+ * ---------------------------------------------------------------------------------------------------- */
+enum {
+  LLB_PROF_GEMM_QKV = 0, LLB_PROF_GEMM_PROJ, LLB_PROF_GEMM_FC1, LLB_PROF_GEMM_FC2, LLB_PROF_GEMM_ADALN,
+  LLB_PROF_GEMM_OTHER, LLB_PROF_ATTENTION, LLB_PROF_LN_MOD_RES, LLB_PROF_DIT_STEP, LLB_PROF_DIT_MISC,
+  LLB_PROF_GIN_AGGREGATE, LLB_PROF_GIN_POOL, LLB_PROF_GIN_GEMM_MLP0, LLB_PROF_GIN_GEMM_MLP4, LLB_PROF_GIN_ROWLN,
+  LLB_PROF_GIN_MISC, LLB_PROF_GIN_GEMM_HEAD, LLB_PROF_GIN_TOPK, LLB_PROF_SLOTS
+};
+int llb_profile_enable(int on);
+int llb_profile_read(int slot, double* total_ms, int64_t* launches);
+const char* llb_profile_slot_name(int slot);
+
+/* ------------------------------------------------------------------------------------------------------
  * tcgen05 GEMM building block:  C[M,N] = act(A[M,K] . W[N,K]^T + bias[N])
  * A, W: bf16 row-major (K contiguous; lda, ldw in elements, multiples of 8); C: bf16 or fp32 row-major.
  * Replaces every nn.Linear on the path (cuBLAS in the reference): graph_decoder/layers.py:47,52,108-111,

@@ -64,6 +64,9 @@ SIGNATURES = {
     "llb_last_error": (C.c_char_p, []),
     "llb_version": (_I, []),
     "llb_arch_check": (_I, [_I]),
+    "llb_profile_enable": (_I, [_I]),
+    "llb_profile_read": (_I, [_I, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "llb_profile_slot_name": (C.c_char_p, [_I]),
     "llb_gemm_bf16": (_I, [_P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "llb_dit_packed_bytes": (_I, [C.POINTER(DitConfig), C.POINTER(_SZ)]),
     "llb_dit_pack_weights": (_I, [C.POINTER(DitConfig), C.POINTER(DitWeights), _P, _SZ, _P]),
@@ -144,3 +147,21 @@ def stream_ptr() -> C.c_void_p:
 def require_cuda(t, name: str):
     if not t.is_cuda:
         raise LlamoleB200Error(f"{name} must live on a CUDA (sm_100) device; llamole_b200 has no CPU path")
+
+
+PROF_SLOTS = 18
+
+
+def profile_enable(on: bool) -> None:
+    check(lib().llb_profile_enable(int(on)), "llb_profile_enable")
+
+
+def profile_read() -> dict:
+    """{slot name: (total_ms, launches)} since the last read; synchronises on the recorded events."""
+    out = {}
+    for i in range(PROF_SLOTS):
+        ms, n = C.c_double(), C.c_int64()
+        check(lib().llb_profile_read(i, C.byref(ms), C.byref(n)), "llb_profile_read")
+        if n.value:
+            out[lib().llb_profile_slot_name(i).decode()] = (ms.value, n.value)
+    return out

@@ -258,9 +258,13 @@ static int dit_forward(llb_dit* h, int t, cudaStream_t s) {
   if (Mtok == 0) return LLB_OK;
   GemmCounters* ctr = &h->ctr;
   // 1. tokens -> embedding -> LayerNorm (shared by both halves)
-  dit_tokens_kernel<<<ceil_div(Mtok, 8), 256, 0, s>>>(h->stX, h->stE, h->mol_off, h->row_mol, h->tok, Mtok, L.N, L.K0);
+  {
+    ProfScope prof(LLB_PROF_DIT_MISC, s);
+    dit_tokens_kernel<<<ceil_div(Mtok, 8), 256, 0, s>>>(h->stX, h->stE, h->mol_off, h->row_mol, h->tok, Mtok, L.N, L.K0);
+  }
   LLB_CUDA_OK(cudaGetLastError());
   h->launches++;
+  ctr->slot = LLB_PROF_GEMM_OTHER;
   float* emb = reinterpret_cast<float*>(h->hbuf);
   LLB_TRY(gemm_bias_act(h->tok, L.K0, h->w<void>(L.x_embed_w), L.K0, nullptr, emb, H, Mtok, H, L.K0, LLB_ACT_NONE, true, s, ctr));
   {
@@ -269,14 +273,19 @@ static int dit_forward(llb_dit* h, int t, cudaStream_t s) {
     a.gamma = h->w<float>(L.x_ln_w), a.beta = h->w<float>(L.x_ln_b);
     a.out_f32 = h->x, a.out_f32_ld = H, a.out_bf16 = h->xb, a.out_bf16_ld = H;
     a.dup_rows = h->passes == 2 ? Mtok : 0;
+    a.prof_slot = LLB_PROF_DIT_MISC;
     LLB_TRY(launch_row_ln(a, s));
     h->launches++;
   }
   // 2. conditioning vector and all adaLN modulations of this step
-  dit_cvec_kernel<<<ceil_div((B + 1) * H, 256), 256, 0, s>>>(h->w<float>(L.c1_table) + (size_t)t * H, h->cinv, h->w<float>(L.c_unc),
+  {
+    ProfScope prof(LLB_PROF_DIT_MISC, s);
+    dit_cvec_kernel<<<ceil_div((B + 1) * H, 256), 256, 0, s>>>(h->w<float>(L.c1_table) + (size_t)t * H, h->cinv, h->w<float>(L.c_unc),
                                                             h->cvec, B, H);
+  }
   LLB_CUDA_OK(cudaGetLastError());
   h->launches++;
+  ctr->slot = LLB_PROF_GEMM_ADALN;
   const int ldh = (D + 1) * H;
   LLB_TRY(gemm_bias_act(h->cvec, H, h->w<void>(L.ada0_w), H, h->w<float>(L.ada0_b), h->hid, ldh, B + 1, ldh, H, LLB_ACT_SILU, false, s, ctr));
   for (int l = 0; l < D; ++l)
@@ -288,11 +297,16 @@ static int dit_forward(llb_dit* h, int t, cudaStream_t s) {
   const float q_scale = 1.4426950408889634f / sqrtf((float)DIT_DH);
   for (int l = 0; l < D; ++l) {
     const float* mod = h->mod + (size_t)l * (B + 1) * 6 * H;
+    ctr->slot = LLB_PROF_GEMM_QKV;
     EpiQKV eq{h->qkv, 3 * H, H, h->w<float>(L.qn_w[l]), h->w<float>(L.qn_b[l]), h->w<float>(L.kn_w[l]), h->w<float>(L.kn_b[l]), q_scale};
-    LLB_TRY((launch_gemm<256, 8>(h->xb, H, h->w<void>(L.qkv_w[l]), H, M, 3 * H, H, eq, s, ctr)));
-    dit_attention_kernel<<<dim3(h->passes * B, L.heads), 128, 0, s>>>(h->qkv, h->attn, h->mol_off, B, Mtok, H);
+    LLB_TRY((launch_gemm<256>(h->xb, H, h->w<void>(L.qkv_w[l]), H, M, 3 * H, H, eq, s, ctr)));
+    {
+      ProfScope prof(LLB_PROF_ATTENTION, s);
+      dit_attention_kernel<<<dim3(h->passes * B, L.heads), 128, 0, s>>>(h->qkv, h->attn, h->mol_off, B, Mtok, H);
+    }
     LLB_CUDA_OK(cudaGetLastError());
     h->launches++;
+    ctr->slot = LLB_PROF_GEMM_PROJ;
     LLB_TRY(gemm_bias_act(h->attn, H, h->w<void>(L.proj_w[l]), H, h->w<float>(L.proj_b[l]), h->y, H, M, H, H, LLB_ACT_NONE, false, s, ctr));
     RowLnArgs a;
     a.in = h->y, a.in_ld = H, a.in_bf16 = true, a.rows = M, a.width = H;
@@ -301,13 +315,16 @@ static int dit_forward(llb_dit* h, int t, cudaStream_t s) {
     a.resid = h->x, a.resid_ld = H, a.out_f32 = h->x, a.out_f32_ld = H, a.out_bf16 = h->xb, a.out_bf16_ld = H;
     LLB_TRY(launch_row_ln(a, s));
     h->launches++;
+    ctr->slot = LLB_PROF_GEMM_FC1;
     LLB_TRY(gemm_bias_act(h->xb, H, h->w<void>(L.fc1_w[l]), H, h->w<float>(L.fc1_b[l]), h->hbuf, F, M, F, H, LLB_ACT_GELU, false, s, ctr));
+    ctr->slot = LLB_PROF_GEMM_FC2;
     LLB_TRY(gemm_bias_act(h->hbuf, F, h->w<void>(L.fc2_w[l]), F, h->w<float>(L.fc2_b[l]), h->y, H, M, H, F, LLB_ACT_NONE, false, s, ctr));
     a.shift = mod + 3 * H, a.scale = mod + 4 * H, a.gate = mod + 5 * H;
     LLB_TRY(launch_row_ln(a, s));
     h->launches++;
   }
   // 4. output MLP (the LayerNorm / modulation / symmetrisation tail lives in the step kernel)
+  ctr->slot = LLB_PROF_GEMM_OTHER;
   LLB_TRY(gemm_bias_act(h->xb, H, h->w<void>(L.out_fc1_w), H, h->w<float>(L.out_fc1_b), h->y, H, M, H, H, LLB_ACT_GELU, false, s, ctr));
   LLB_TRY(gemm_bias_act(h->y, H, h->w<void>(L.out_fc2_w), H, h->w<float>(L.out_fc2_b), h->raw, h->raw_ld, M, L.d0, H, LLB_ACT_NONE, true, s, ctr));
   return LLB_OK;
@@ -320,7 +337,10 @@ static int dit_launch_step(llb_dit* h, DitStepArgs& a, cudaStream_t s) {
     LLB_CUDA_OK(cudaFuncSetAttribute(dit_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  dit_step_kernel<<<h->B, 256, smem, s>>>(a, h->tables);
+  {
+    ProfScope prof(LLB_PROF_DIT_STEP, s);
+    dit_step_kernel<<<h->B, 256, smem, s>>>(a, h->tables);
+  }
   LLB_CUDA_OK(cudaGetLastError());
   h->launches++;
   return LLB_OK;

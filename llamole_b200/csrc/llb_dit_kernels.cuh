@@ -16,39 +16,38 @@ constexpr int DIT_MAXN = 64;
 // ------------------------------------------------------------------------------------------------
 struct EpiQKV {
   static constexpr int CHUNK = 64;
-  __nv_bfloat16* out;  // (M, 3H)
-  int ld, H;
+  static constexpr bool OUT_F32 = false;
+  void* C;  // (M, 3H) bf16
+  int ldc;
+  int H;
   const float *qw, *qb, *kw, *kb;  // (64) each
   float q_scale;                   // dh^-0.5 * log2(e)
-  __device__ __forceinline__ void operator()(int row, int col0, const float* acc, int M, int N) const {
+  __device__ __forceinline__ void transform(int row, int col0, float* v, int M, int N) const {
     const int which = col0 / H;  // 0 q, 1 k, 2 v
-    float v[64];
     if (which < 2) {
       float s = 0.f;
 #pragma unroll
-      for (int i = 0; i < 64; ++i) s += acc[i];
+      for (int i = 0; i < 64; ++i) s += v[i];
       const float mean = s * (1.0f / 64.0f);
       float q = 0.f;
 #pragma unroll
       for (int i = 0; i < 64; ++i) {
-        const float d = acc[i] - mean;
+        const float d = v[i] - mean;
         q = fmaf(d, d, q);
       }
       const float rstd = rsqrtf(q * (1.0f / 64.0f) + 1e-5f);
-      const float* w = which == 0 ? qw : kw;
-      const float* b = which == 0 ? qb : kb;
+      const float4* w = reinterpret_cast<const float4*>(which == 0 ? qw : kw);
+      const float4* b = reinterpret_cast<const float4*>(which == 0 ? qb : kb);
       const float post = which == 0 ? q_scale : 1.0f;
 #pragma unroll
-      for (int i = 0; i < 64; ++i) v[i] = ((acc[i] - mean) * rstd * __ldg(w + i) + __ldg(b + i)) * post;
-    } else {
-#pragma unroll
-      for (int i = 0; i < 64; ++i) v[i] = acc[i];
+      for (int i = 0; i < 16; ++i) {
+        const float4 w4 = __ldg(w + i), b4 = __ldg(b + i);
+        v[4 * i] = ((v[4 * i] - mean) * rstd * w4.x + b4.x) * post;
+        v[4 * i + 1] = ((v[4 * i + 1] - mean) * rstd * w4.y + b4.y) * post;
+        v[4 * i + 2] = ((v[4 * i + 2] - mean) * rstd * w4.z + b4.z) * post;
+        v[4 * i + 3] = ((v[4 * i + 3] - mean) * rstd * w4.w + b4.w) * post;
+      }
     }
-    __nv_bfloat16* o = out + (size_t)row * ld + col0;
-#pragma unroll
-    for (int i = 0; i < 64; i += 8)
-      *reinterpret_cast<uint4*>(o + i) = make_uint4(pack_bf16x2(v[i], v[i + 1]), pack_bf16x2(v[i + 2], v[i + 3]),
-                                                    pack_bf16x2(v[i + 4], v[i + 5]), pack_bf16x2(v[i + 6], v[i + 7]));
   }
 };
 
@@ -126,15 +125,27 @@ __global__ void __launch_bounds__(128) dit_attention_kernel(const __nv_bfloat16*
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ld = 3 * H;
   const int npad = (n + 15) & ~15;
-  // load q, k, v head slices (16 B per thread per access); rows >= n are zero
-  for (int idx = tid; idx < npad * 8 * 3; idx += 128) {
-    const int mat = idx / (npad * 8);
-    const int rem = idx % (npad * 8);
-    const int r = rem >> 3, ch = rem & 7;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (r < n) v = *reinterpret_cast<const uint4*>(qkv + (size_t)(row0 + r) * ld + mat * H + head * DIT_DH + ch * 8);
-    __nv_bfloat16* dst = (mat == 0 ? sQ : (mat == 1 ? sK : sV)) + r * ATT_LD + ch * 8;
-    *reinterpret_cast<uint4*>(dst) = v;
+  // load q, k, v head slices: thread -> (row tid/8 + 16 it, 16-byte piece tid%8); rows in [n, npad) are zero
+  {
+    const int r0l = tid >> 3, ch = tid & 7;
+    const __nv_bfloat16* src = qkv + (size_t)row0 * ld + head * DIT_DH + ch * 8;
+    uint4 v[3][4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int r = r0l + 16 * it;
+#pragma unroll
+      for (int mat = 0; mat < 3; ++mat)
+        v[mat][it] = r < n ? __ldg(reinterpret_cast<const uint4*>(src + (size_t)r * ld + mat * H)) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int r = r0l + 16 * it;
+      if (r < npad) {
+        *reinterpret_cast<uint4*>(sQ + r * ATT_LD + ch * 8) = v[0][it];
+        *reinterpret_cast<uint4*>(sK + r * ATT_LD + ch * 8) = v[1][it];
+        *reinterpret_cast<uint4*>(sV + r * ATT_LD + ch * 8) = v[2][it];
+      }
+    }
   }
   __syncthreads();
   if (warp * 16 >= n) return;
@@ -208,12 +219,24 @@ __global__ void __launch_bounds__(128) dit_attention_kernel(const __nv_bfloat16*
   }
   const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
   const int g = lane >> 2;
-  const int r0 = warp * 16 + g, r1 = r0 + 8;
+  // stage the warp's 16 x 64 output tile in its own (already consumed) Q rows, then write 16-byte pieces so that
+  // 8 lanes cover one 128-byte row segment (the direct fragment layout would issue 16-byte-per-row stores)
+  __nv_bfloat16* sO = sQ + warp * 16 * ATT_LD;
+  __syncwarp();
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const int col = head * DIT_DH + j * 8 + t4 * 2;
-    if (r0 < n) *reinterpret_cast<uint32_t*>(out + (size_t)(row0 + r0) * H + col) = pack_bf16x2(o[j][0] * inv0, o[j][1] * inv0);
-    if (r1 < n) *reinterpret_cast<uint32_t*>(out + (size_t)(row0 + r1) * H + col) = pack_bf16x2(o[j][2] * inv1, o[j][3] * inv1);
+    const int col = j * 8 + t4 * 2;
+    *reinterpret_cast<uint32_t*>(sO + g * ATT_LD + col) = pack_bf16x2(o[j][0] * inv0, o[j][1] * inv0);
+    *reinterpret_cast<uint32_t*>(sO + (g + 8) * ATT_LD + col) = pack_bf16x2(o[j][2] * inv1, o[j][3] * inv1);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int p = lane + 32 * i;
+    const int r = p >> 3, ch = p & 7;
+    const int grow = warp * 16 + r;
+    if (grow < n)
+      *reinterpret_cast<uint4*>(out + (size_t)(row0 + grow) * H + head * DIT_DH + ch * 8) = *reinterpret_cast<const uint4*>(sO + r * ATT_LD + ch * 8);
   }
 }
 

@@ -3,13 +3,16 @@
 // A (activations) and W (nn.Linear weight, (out,in)) are both K-major bf16, so both operands go through TMA
 // with the 128-byte swizzle straight into the UMMA shared-memory layout.
 //
-// Persistent, warp-specialised CTA (one per SM):
-//   warp 0      TMA producer: fills a ring of STAGES {A 128x64, W BNx64} tiles, arms full[] with expect_tx
-//   warp 1      MMA issuer: one elected lane issues tcgen05.mma (M=128, N=BN, K=16) x4 per stage and
+// Persistent, warp-specialised CTA (one per SM), 12 warps:
+//   warps 0..7  epilogue: tcgen05.ld their TMEM lane quarter (warp % 4), run the fused epilogue functor, stage the
+//               converted chunk in swizzled shared memory and hand it to a TMA store (full 128-byte lines, no LSU
+//               pressure), then release the accumulator stage (tmem_empty[acc]) so the next tile's MMAs overlap
+//   warp 8      TMA producer: fills a ring of STAGES {A 128x64, W BNx64} tiles, arms full[] with expect_tx
+//   warp 9      MMA issuer: one elected lane issues tcgen05.mma (M=128, N=BN, K=16) x4 per stage and
 //               tcgen05.commit's the stage's empty[] barrier; after the last k-block commits tmem_full[acc]
-//   warp 2      TMEM allocator (2 accumulator stages x BN fp32 columns)
-//   warps 4..   epilogue: tcgen05.ld their lane quarter, run the fused epilogue functor, store to global,
-//               then release the accumulator stage (tmem_empty[acc]) so the next tile's MMAs overlap
+//   warp 10     TMEM allocator (2 accumulator stages x BN fp32 columns)
+// The producer / issuer warps carry the highest warp ids on their scheduler: the issue arbiter prefers high ids,
+// so a busy epilogue can never starve the single thread that feeds the tensor pipe.
 // Tiles are walked n-fastest so that the CTAs in flight share A tiles through L2 and W stays L2-resident.
 #pragma once
 #include "llb_common.cuh"
@@ -18,6 +21,9 @@ namespace llb {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
+constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 32 * (GEMM_EPI_WARPS + 4);
+constexpr int GEMM_STAGING_PER_WARP = 4096;  // 32 rows x 128 B (or 2 x 32 rows x 64 B)
 
 template <int BN>
 struct GemmCfg {
@@ -26,25 +32,46 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = 2 * BN;  // 512 / 256 / 128
+  static constexpr int STAGING_BYTES = GEMM_EPI_WARPS * GEMM_STAGING_PER_WARP;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment slack
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + 1024;  // +1024: alignment slack
 };
 
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // Epilogue functor contract:
-//   static constexpr int CHUNK (32 or 64): consecutive columns handed over per call
-//   __device__ void operator()(int row, int col0, const float* acc, int M, int N) const
-//     row < M guaranteed; columns col0 .. col0+CHUNK-1 may exceed N (functor guards).
-template <int BN, int EPI_WARPS, class Epi>
-__global__ void __launch_bounds__(128 + 32 * EPI_WARPS, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
-                    int K, Epi epi) {
+//   static constexpr int  CHUNK   (32 or 64): consecutive accumulator columns handed over per call
+//   static constexpr bool OUT_F32 : element type of C (fp32 or bf16); CHUNK * sizeof(elem) <= 128
+//   void* C; int ldc;              output matrix (row-major)
+//   __device__ void transform(int row, int col0, float* v, int M, int N) const   -- in place on v[CHUNK];
+//     called for every row of the tile, including rows >= M (their results are never stored).
+template <int BN, bool TMA_STORE, class Epi>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, int M, int N, int K, Epi epi) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int ELEM = Epi::OUT_F32 ? 4 : 2;
+  constexpr int ROW_BYTES = Epi::CHUNK * ELEM;            // 64 or 128
+  static_assert(ROW_BYTES == 64 || ROW_BYTES == 128, "epilogue chunk must be 64 or 128 bytes per row");
+  constexpr int NBUF = GEMM_STAGING_PER_WARP / (32 * ROW_BYTES);  // 2 or 1 staging buffers per warp
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smA = smem;
   uint8_t* smB = smem + STAGES * Cfg::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* smStage = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smStage + Cfg::STAGING_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* tmem_full = bars + 2 * STAGES;
@@ -58,26 +85,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int num_tiles = num_m * num_n;
   const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == GEMM_EPI_WARPS && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (TMA_STORE) tma_prefetch_desc(&tmC);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], EPI_WARPS);
+      mbar_init(&tmem_empty[a], GEMM_EPI_WARPS);
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (warp == GEMM_EPI_WARPS + 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == GEMM_EPI_WARPS) {
     // ---------------- TMA producer ----------------
     if (lane == 0) {
       int stage = 0;
@@ -97,7 +125,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == GEMM_EPI_WARPS + 1) {
     // ---------------- MMA issuer ----------------
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
@@ -132,13 +160,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp < GEMM_EPI_WARPS) {
     // ---------------- epilogue ----------------
-    const int ew = warp - 4;
-    const int quarter = warp & 3;               // TMEM lane quarter this warp may access
-    constexpr int COL_GROUPS = EPI_WARPS / 4;   // warps sharing a quarter split the columns
-    constexpr int COLS_PER_WARP = BN / COL_GROUPS;
-    const int cg = ew >> 2;
+    const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
+    constexpr int COLS_PER_WARP = BN / (GEMM_EPI_WARPS / 4);
+    const int cg = warp >> 2;                        // warps sharing a quarter split the columns
+    uint8_t* stg = smStage + warp * GEMM_STAGING_PER_WARP;
+    int buf = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -151,11 +179,48 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       float v[Epi::CHUNK];
 #pragma unroll 1
       for (int c = 0; c < COLS_PER_WARP; c += Epi::CHUNK) {
-        if (n0 + cg * COLS_PER_WARP + c < N) {   // warp-uniform
-          tmem_ld32(t_row + c, v);
-          if (Epi::CHUNK == 64) tmem_ld32(t_row + c + 32, v + 32);
-          tmem_ld_wait();
-          if (row < M) epi(row, n0 + cg * COLS_PER_WARP + c, v, M, N);
+        const int col0 = n0 + cg * COLS_PER_WARP + c;
+        if (col0 >= N) break;   // warp-uniform
+        tmem_ld32(t_row + c, v);
+        if (Epi::CHUNK == 64) tmem_ld32(t_row + c + 32, v + 32);
+        tmem_ld_wait();
+        epi.transform(row, col0, v, M, N);
+        if (TMA_STORE) {
+          uint8_t* dst = stg + buf * (32 * ROW_BYTES);
+          if (lane == 0) bulk_wait_read<NBUF - 1>();   // the buffer about to be overwritten has been read out
+          __syncwarp();
+          // row `lane` of the staging tile, 16-byte pieces XOR-swizzled exactly like the C tensor map
+          uint8_t* rowp = dst + lane * ROW_BYTES;
+          const int sw = ROW_BYTES == 128 ? (lane & 7) : ((lane >> 1) & 3);
+#pragma unroll
+          for (int p = 0; p < ROW_BYTES / 16; ++p) {
+            uint4 q;
+            if (Epi::OUT_F32) {
+              q = make_uint4(__float_as_uint(v[4 * p]), __float_as_uint(v[4 * p + 1]), __float_as_uint(v[4 * p + 2]),
+                             __float_as_uint(v[4 * p + 3]));
+            } else {
+              q = make_uint4(pack_bf16x2(v[8 * p], v[8 * p + 1]), pack_bf16x2(v[8 * p + 2], v[8 * p + 3]),
+                             pack_bf16x2(v[8 * p + 4], v[8 * p + 5]), pack_bf16x2(v[8 * p + 6], v[8 * p + 7]));
+            }
+            *reinterpret_cast<uint4*>(rowp + ((p ^ sw) << 4)) = q;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmC, dst, col0, m0 + quarter * 32);
+            bulk_commit();
+          }
+          buf = (buf + 1) % NBUF;
+        } else if (row < M) {
+          if (Epi::OUT_F32) {
+            float* out = reinterpret_cast<float*>(epi.C) + (size_t)row * epi.ldc + col0;
+            for (int i = 0; i < Epi::CHUNK; ++i)
+              if (col0 + i < N) out[i] = v[i];
+          } else {
+            __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(epi.C) + (size_t)row * epi.ldc + col0;
+            for (int i = 0; i < Epi::CHUNK; ++i)
+              if (col0 + i < N) out[i] = __float2bfloat16(v[i]);
+          }
         }
       }
       tc_fence_before();
@@ -166,10 +231,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         acc_phase ^= 1;
       }
     }
+    if (TMA_STORE && lane == 0) bulk_wait_all();
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == GEMM_EPI_WARPS + 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
@@ -178,14 +244,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // ------------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------------
-// 2-D bf16 tensor map: inner dim = K (contiguous), outer dim = rows; box = 64 x box_rows; 128B swizzle.
-int make_tensor_map_bf16(CUtensorMap* out, const void* ptr, int rows, int cols, int ld_elems, int box_rows);
+// 2-D tensor map: inner dim = cols (contiguous), outer dim = rows; box = box_cols x box_rows;
+// swizzle_bytes in {64, 128} must equal box_cols * elem_bytes.
+int make_tensor_map_2d(CUtensorMap* out, const void* ptr, int elem_bytes, int rows, int cols, int ld_elems, int box_cols,
+                       int box_rows, int swizzle_bytes);
 
 struct GemmCounters {
   int64_t launches = 0;
+  int slot = LLB_PROF_GEMM_OTHER;  // profiling slot charged for the next launches
 };
 
-template <int BN, int EPI_WARPS, class Epi>
+template <int BN, class Epi>
 int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const Epi& epi,
                 cudaStream_t stream, GemmCounters* ctr = nullptr) {
   using Cfg = GemmCfg<BN>;
@@ -193,18 +262,27 @@ int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, in
   LLB_CHECK_ARG(K > 0 && lda % 8 == 0 && ldw % 8 == 0, "gemm: K=%d lda=%d ldw=%d (ld must be a multiple of 8)", K, lda, ldw);
   LLB_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0,
                 "gemm: operands must be 16-byte aligned");
-  CUtensorMap tmA, tmB;
-  LLB_TRY(make_tensor_map_bf16(&tmA, A, M, K, lda, GEMM_BM));
-  LLB_TRY(make_tensor_map_bf16(&tmB, W, N, K, ldw, BN));
-  auto kern = gemm_tcgen05_kernel<BN, EPI_WARPS, Epi>;
-  static bool configured = false;  // per template instantiation
-  if (!configured) {
-    LLB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured = true;
-  }
+  constexpr int ELEM = Epi::OUT_F32 ? 4 : 2;
+  CUtensorMap tmA, tmB, tmC;
+  LLB_TRY(make_tensor_map_2d(&tmA, A, 2, M, K, lda, GEMM_BK, GEMM_BM, 128));
+  LLB_TRY(make_tensor_map_2d(&tmB, W, 2, N, K, ldw, GEMM_BK, BN, 128));
+  const bool tma_store = ((size_t)epi.ldc * ELEM) % 16 == 0 && (reinterpret_cast<uintptr_t>(epi.C) & 15) == 0;
+  if (tma_store) LLB_TRY(make_tensor_map_2d(&tmC, epi.C, ELEM, M, N, epi.ldc, Epi::CHUNK, 32, Epi::CHUNK * ELEM));
+  else tmC = tmA;
   const int tiles = ceil_div(M, GEMM_BM) * ceil_div(N, BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, 128 + 32 * EPI_WARPS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, epi);
+  static bool configured[2] = {false, false};  // per template instantiation
+  auto launch = [&](auto kern, int which) -> int {
+    if (!configured[which]) {
+      LLB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+      configured[which] = true;
+    }
+    ProfScope prof(ctr ? ctr->slot : LLB_PROF_GEMM_OTHER, stream);
+    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, M, N, K, epi);
+    return LLB_OK;
+  };
+  if (tma_store) LLB_TRY(launch(gemm_tcgen05_kernel<BN, true, Epi>, 0));
+  else LLB_TRY(launch(gemm_tcgen05_kernel<BN, false, Epi>, 1));
   LLB_CUDA_OK(cudaGetLastError());
   if (ctr) ctr->launches++;
   return LLB_OK;
@@ -215,48 +293,35 @@ int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, in
 // ------------------------------------------------------------------------------------------------
 template <int ACT>
 __device__ __forceinline__ float apply_act(float x) {
-  if (ACT == LLB_ACT_GELU) return gelu_erf(x);
+  if (ACT == LLB_ACT_GELU) return gelu_fast(x);
   if (ACT == LLB_ACT_SILU) return silu(x);
   if (ACT == LLB_ACT_SOFTSIGN) return softsign(x);
   return x;
 }
 
 // C = act(acc + bias) -> bf16 or fp32 row-major.
-template <int ACT, bool OUT_F32>
+template <int ACT, bool F32>
 struct EpiBiasAct {
   static constexpr int CHUNK = 32;
+  static constexpr bool OUT_F32 = F32;
   void* C;
-  const float* bias;  // may be null
   int ldc;
-  __device__ __forceinline__ void operator()(int row, int col0, const float* acc, int M, int N) const {
-    float v[32];
+  const float* bias;  // may be null
+  __device__ __forceinline__ void transform(int row, int col0, float* v, int M, int N) const {
+    if (bias != nullptr) {
+      if (col0 + 32 <= N) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const int c = col0 + i;
-      float b = (bias != nullptr && c < N) ? __ldg(bias + c) : 0.0f;
-      v[i] = apply_act<ACT>(acc[i] + b);
-    }
-    if (OUT_F32) {
-      float* out = reinterpret_cast<float*>(C) + (size_t)row * ldc + col0;
-      if (col0 + 32 <= N && (ldc & 3) == 0) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(out + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        for (int i = 0; i < 32; i += 4) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col0 + i));
+          v[i] += b.x, v[i + 1] += b.y, v[i + 2] += b.z, v[i + 3] += b.w;
+        }
       } else {
-        for (int i = 0; i < 32; ++i)
-          if (col0 + i < N) out[i] = v[i];
-      }
-    } else {
-      __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(C) + (size_t)row * ldc + col0;
-      if (col0 + 32 <= N && (ldc & 7) == 0) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 8)
-          *reinterpret_cast<uint4*>(out + i) = make_uint4(pack_bf16x2(v[i], v[i + 1]), pack_bf16x2(v[i + 2], v[i + 3]),
-                                                          pack_bf16x2(v[i + 4], v[i + 5]), pack_bf16x2(v[i + 6], v[i + 7]));
-      } else {
-        for (int i = 0; i < 32; ++i)
-          if (col0 + i < N) out[i] = __float2bfloat16(v[i]);
+        for (int i = 0; i < 32; ++i) v[i] += (col0 + i < N) ? __ldg(bias + col0 + i) : 0.0f;
       }
     }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = apply_act<ACT>(v[i]);
   }
 };
 

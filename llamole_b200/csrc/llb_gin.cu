@@ -212,10 +212,10 @@ __global__ void __launch_bounds__(256) gin_aggregate_kernel(const float* __restr
       const uint4 u = *reinterpret_cast<const uint4*>(hb + (size_t)j * H + c);
       const float4 e0 = *reinterpret_cast<const float4*>(bond_emb + (size_t)et * H + c);
       const float4 e1 = *reinterpret_cast<const float4*>(bond_emb + (size_t)et * H + c + 4);
-      acc[0] += gelu_erf(bf16_lo(u.x) + e0.x), acc[1] += gelu_erf(bf16_hi(u.x) + e0.y);
-      acc[2] += gelu_erf(bf16_lo(u.y) + e0.z), acc[3] += gelu_erf(bf16_hi(u.y) + e0.w);
-      acc[4] += gelu_erf(bf16_lo(u.z) + e1.x), acc[5] += gelu_erf(bf16_hi(u.z) + e1.y);
-      acc[6] += gelu_erf(bf16_lo(u.w) + e1.z), acc[7] += gelu_erf(bf16_hi(u.w) + e1.w);
+      acc[0] += gelu_fast(bf16_lo(u.x) + e0.x), acc[1] += gelu_fast(bf16_hi(u.x) + e0.y);
+      acc[2] += gelu_fast(bf16_lo(u.y) + e0.z), acc[3] += gelu_fast(bf16_hi(u.y) + e0.w);
+      acc[4] += gelu_fast(bf16_lo(u.z) + e1.x), acc[5] += gelu_fast(bf16_hi(u.z) + e1.y);
+      acc[6] += gelu_fast(bf16_lo(u.w) + e1.z), acc[7] += gelu_fast(bf16_hi(u.w) + e1.w);
     }
     *reinterpret_cast<uint4*>(out + (size_t)i * H + c) =
         make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
@@ -430,16 +430,20 @@ static int gin_scan(llb_gin* g, cudaStream_t s) {
 }
 
 static int gin_mlp4(llb_gin* g, const __nv_bfloat16* in, int rows, size_t w0, size_t b0, size_t lnw, size_t lnb, size_t w4, size_t b4,
-                    int hidden, int out_f, __nv_bfloat16* zbuf, float* out, int out_ld, cudaStream_t s) {
+                    int hidden, int out_f, __nv_bfloat16* zbuf, float* out, int out_ld, cudaStream_t s, int slot0 = LLB_PROF_GIN_MISC,
+                    int slot4 = LLB_PROF_GIN_MISC) {
   // Linear -> LayerNorm(hidden) -> GELU -> Linear  (the 4H MLP of GINConv / virtual node / heads)
   const int H = g->G.H;
+  g->ctr.slot = slot0;
   LLB_TRY(gemm_bias_act(in, H, g->w<void>(w0), H, g->w<float>(b0), zbuf, hidden, rows, hidden, H, LLB_ACT_NONE, false, s, &g->ctr));
   RowLnArgs a;
   a.in = zbuf, a.in_ld = hidden, a.in_bf16 = true, a.rows = rows, a.width = hidden;
   a.gamma = g->w<float>(lnw), a.beta = g->w<float>(lnb), a.act = LLB_ACT_GELU;
   a.out_bf16 = zbuf, a.out_bf16_ld = hidden;
+  a.prof_slot = LLB_PROF_GIN_ROWLN;
   LLB_TRY(launch_row_ln(a, s));
   g->launches++;
+  g->ctr.slot = slot4;
   return gemm_bias_act(zbuf, hidden, g->w<void>(w4), hidden, g->w<float>(b4), out, out_ld, rows, out_f, hidden, LLB_ACT_NONE, true, s, &g->ctr);
 }
 
@@ -458,19 +462,26 @@ static int gin_trunk(llb_gin* g, const float* c, cudaStream_t s) {
         c, g->w<float>(G.text_drop), g->ctext, B, G.tdim);
     LLB_CUDA_OK(cudaGetLastError());
     g->launches++;
+    g->ctr.slot = LLB_PROF_GIN_MISC;
     for (int l = 0; l < L; ++l)
       LLB_TRY(gemm_bias_act(g->ctext, G.tdim, g->w<void>(G.adapter_w[l]), G.tdim, g->w<float>(G.adapter_b[l]),
                             g->mod + (size_t)l * B * 3 * H, 3 * H, B, 3 * H, G.tdim, LLB_ACT_NONE, true, s, &g->ctr));
   }
   for (int l = 0; l < L; ++l) {
     const bool last = (l == L - 1);
-    gin_aggregate_kernel<<<ceil_div(n, 8), 256, 0, s>>>(g->h, g->hb, g->rowptr, g->col, g->eid, g->w<float>(G.bond_emb[l]),
-                                                        g->w<float>(G.eps[l]), g->agg, n, H);
+    {
+      ProfScope prof(LLB_PROF_GIN_AGGREGATE, s);
+      gin_aggregate_kernel<<<ceil_div(n, 8), 256, 0, s>>>(g->h, g->hb, g->rowptr, g->col, g->eid, g->w<float>(G.bond_emb[l]),
+                                                          g->w<float>(G.eps[l]), g->agg, n, H);
+    }
     LLB_CUDA_OK(cudaGetLastError());
     g->launches++;
     if (!last) {
       // virtual node of the next layer from the max-pool of this layer's INPUT (model.py:148 / :343)
-      gin_pool_kernel<<<dim3(B, ceil_div(H, 256)), 256, 0, s>>>(g->h, g->graph_ptr, H, 1, nullptr, g->pool_b);
+      {
+        ProfScope prof(LLB_PROF_GIN_POOL, s);
+        gin_pool_kernel<<<dim3(B, ceil_div(H, 256)), 256, 0, s>>>(g->h, g->graph_ptr, H, 1, nullptr, g->pool_b);
+      }
       LLB_CUDA_OK(cudaGetLastError());
       g->launches++;
       LLB_TRY(gin_mlp4(g, g->pool_b, B, G.vn0_w[l], G.vn0_b[l], G.vn_ln_w[l], G.vn_ln_b[l], G.vn4_w[l], G.vn4_b[l], 4 * H, H, g->vz,
@@ -478,11 +489,12 @@ static int gin_trunk(llb_gin* g, const float* c, cudaStream_t s) {
       RowLnArgs a;
       a.in = g->vu, a.in_ld = H, a.rows = B, a.width = H, a.normalize = false;
       a.resid = g->vn_cur, a.resid_ld = H, a.out_f32 = g->vn_next, a.out_f32_ld = H;
+      a.prof_slot = LLB_PROF_GIN_MISC;
       LLB_TRY(launch_row_ln(a, s));
       g->launches++;
     }
     LLB_TRY(gin_mlp4(g, g->agg, n, G.mlp0_w[l], G.mlp0_b[l], G.mlp_ln_w[l], G.mlp_ln_b[l], G.mlp4_w[l], G.mlp4_b[l], 4 * H, H, g->z,
-                     g->u, H, s));
+                     g->u, H, s, LLB_PROF_GIN_GEMM_MLP0, LLB_PROF_GIN_GEMM_MLP4));
     RowLnArgs a;
     a.in = g->u, a.in_ld = H, a.rows = n, a.width = H;
     a.row_group = g->batch32;
@@ -496,11 +508,15 @@ static int gin_trunk(llb_gin* g, const float* c, cudaStream_t s) {
     a.resid = g->h, a.resid_ld = H;
     if (!last) a.addvec = g->vn_next, a.addvec_ld = H;
     a.out_f32 = g->h, a.out_f32_ld = H, a.out_bf16 = g->hb, a.out_bf16_ld = H;
+    a.prof_slot = LLB_PROF_GIN_ROWLN;
     LLB_TRY(launch_row_ln(a, s));
     g->launches++;
     if (!last) std::swap(g->vn_cur, g->vn_next);
   }
-  gin_pool_kernel<<<dim3(B, ceil_div(H, 256)), 256, 0, s>>>(g->h, g->graph_ptr, H, 0, g->pooled, g->pooled_b);
+  {
+    ProfScope prof(LLB_PROF_GIN_POOL, s);
+    gin_pool_kernel<<<dim3(B, ceil_div(H, 256)), 256, 0, s>>>(g->h, g->graph_ptr, H, 0, g->pooled, g->pooled_b);
+  }
   LLB_CUDA_OK(cudaGetLastError());
   g->launches++;
   return LLB_OK;
@@ -640,10 +656,11 @@ int llb_gin_encoder_forward(llb_gin* g, float* out, float* pooled_or_null, llb_s
   LLB_TRY(gin_trunk(g, nullptr, s));
   if (pooled_or_null) LLB_CUDA_OK(cudaMemcpyAsync(pooled_or_null, g->pooled, (size_t)g->B * G.H * 4, cudaMemcpyDeviceToDevice, s));
   LLB_TRY(gin_mlp4(g, g->pooled_b, g->B, G.head0_w, G.head0_b, G.head_ln_w, G.head_ln_b, G.head4_w, G.head4_b, G.HH, G.HO, g->hz,
-                   g->head_out, G.H, s));
+                   g->head_out, G.H, s, LLB_PROF_GIN_GEMM_HEAD, LLB_PROF_GIN_GEMM_HEAD));
   RowLnArgs a;
   a.in = g->head_out, a.in_ld = G.H, a.rows = g->B, a.width = G.H, a.normalize = false, a.l2_normalize = true;
   a.out_f32 = out, a.out_f32_ld = G.H;
+  a.prof_slot = LLB_PROF_GIN_MISC;
   LLB_TRY(launch_row_ln(a, s));
   g->launches++;
   return LLB_OK;
@@ -652,12 +669,14 @@ int llb_gin_encoder_forward(llb_gin* g, float* out, float* pooled_or_null, llb_s
 static int gin_head_hidden(llb_gin* g, cudaStream_t s) {
   // decoder.0 -> LayerNorm -> GELU, result (B,4H) bf16 in g->hz
   const GinLayout& G = g->G;
+  g->ctr.slot = LLB_PROF_GIN_GEMM_HEAD;
   LLB_TRY(gemm_bias_act(g->pooled_b, G.H, g->w<void>(G.head0_w), G.H, g->w<float>(G.head0_b), g->hz, G.HH, g->B, G.HH, G.H,
                         LLB_ACT_NONE, false, s, &g->ctr));
   RowLnArgs a;
   a.in = g->hz, a.in_ld = G.HH, a.in_bf16 = true, a.rows = g->B, a.width = G.HH;
   a.gamma = g->w<float>(G.head_ln_w), a.beta = g->w<float>(G.head_ln_b), a.act = LLB_ACT_GELU;
   a.out_bf16 = g->hz, a.out_bf16_ld = G.HH;
+  a.prof_slot = LLB_PROF_GIN_ROWLN;
   LLB_TRY(launch_row_ln(a, s));
   g->launches++;
   return LLB_OK;
@@ -685,6 +704,7 @@ int llb_gin_predictor_topk(llb_gin* g, const float* c, int k, float* topk_prob, 
     const int rows = g->B - r0 < g->chunk_rows ? g->B - r0 : g->chunk_rows;
     LLB_TRY(gemm_bias_act(g->hz + (size_t)r0 * G.HH, G.HH, g->w<void>(G.head4_w), G.HH, g->w<float>(G.head4_b), g->logits_ws, G.out_dim,
                           rows, G.out_dim, G.HH, LLB_ACT_NONE, true, s, &g->ctr));
+    ProfScope prof(LLB_PROF_GIN_TOPK, s);
     gin_topk_kernel<<<rows, 1024, 0, s>>>(g->logits_ws, G.out_dim, G.out_dim, k, topk_prob + (size_t)r0 * k, topk_idx + (size_t)r0 * k);
     LLB_CUDA_OK(cudaGetLastError());
     g->launches++;

@@ -21,7 +21,15 @@ struct RowLnDev {
   int out_bf16_ld, dup_rows, l2_normalize;
 };
 
-__device__ __forceinline__ float4 load4(const void* base, int is_bf16, size_t idx) {
+// Compile-time feature mask of the register-resident kernel.  F_RUNTIME keeps every test on the runtime
+// descriptor (cold variants); the hot variants are instantiated with the exact mask so that the body is
+// straight-line code and the compiler can hoist every load above the reductions.
+enum : unsigned {
+  F_IN_BF16 = 1u << 0, F_NORM = 1u << 1, F_GAMMA = 1u << 2, F_MOD = 1u << 3, F_GELU = 1u << 4, F_GATE = 1u << 5,
+  F_RESID = 1u << 6, F_ADDVEC = 1u << 7, F_OUT_F32 = 1u << 8, F_OUT_BF16 = 1u << 9, F_RUNTIME = 1u << 31
+};
+
+__device__ __forceinline__ float4 load4(const void* base, bool is_bf16, size_t idx) {
   if (is_bf16) {
     const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(base) + idx);
     return make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
@@ -31,14 +39,14 @@ __device__ __forceinline__ float4 load4(const void* base, int is_bf16, size_t id
 
 __device__ __forceinline__ float act_rt(float x, int act) {
   switch (act) {
-    case LLB_ACT_GELU: return gelu_erf(x);
+    case LLB_ACT_GELU: return gelu_fast(x);
     case LLB_ACT_SILU: return silu(x);
     case LLB_ACT_SOFTSIGN: return softsign(x);
   }
   return x;
 }
 
-// One warp per row; the row is re-read from L1/L2 for the second and third sweep (<= 16 KB per row).
+// Fallback for widths that are not a multiple of 128: one warp per row, three sweeps over L1/L2.
 __global__ void __launch_bounds__(256) row_ln_kernel(RowLnDev a) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -101,6 +109,122 @@ __global__ void __launch_bounds__(256) row_ln_kernel(RowLnDev a) {
   }
 }
 
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// Register-resident variant: the row (NCH float4 per lane, width = 128 * NCH) is read from global exactly once.
+template <int NCH, unsigned F>
+__global__ void __launch_bounds__(256) row_ln_reg_kernel(RowLnDev a) {
+  constexpr bool RT = (F & F_RUNTIME) != 0;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= a.rows) return;
+  const bool in_bf16 = RT ? a.in_bf16 != 0 : (F & F_IN_BF16) != 0;
+  const bool norm = RT ? a.normalize != 0 : (F & F_NORM) != 0;
+  const bool l2n = RT ? a.l2_normalize != 0 : false;
+  const bool has_gamma = RT ? a.gamma != nullptr : (F & F_GAMMA) != 0;
+  const bool has_mod = RT ? a.scale != nullptr : (F & F_MOD) != 0;
+  const bool has_gate = RT ? a.gate != nullptr : (F & F_GATE) != 0;
+  const bool has_resid = RT ? a.resid != nullptr : (F & F_RESID) != 0;
+  const bool has_add = RT ? a.addvec != nullptr : (F & F_ADDVEC) != 0;
+  const bool out32 = RT ? a.out_f32 != nullptr : (F & F_OUT_F32) != 0;
+  const bool out16 = RT ? a.out_bf16 != nullptr : (F & F_OUT_BF16) != 0;
+  const int dup = RT ? a.dup_rows : 0;
+  const size_t in_off = (size_t)row * a.in_ld;
+  float4 v[NCH];
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) v[k] = load4(a.in, in_bf16, in_off + lane * 4 + k * 128);
+  // the residual is fetched together with the row (one exposed DRAM latency per row)
+  constexpr int NRES = (NCH <= 8 && !RT && (F & F_RESID)) ? NCH : 1;
+  float4 res[NRES];
+  if (NRES == NCH && has_resid) {
+#pragma unroll
+    for (int k = 0; k < NRES; ++k) res[k] = *reinterpret_cast<const float4*>(a.resid + (size_t)row * a.resid_ld + lane * 4 + k * 128);
+  }
+  const int g = a.row_group ? a.row_group[row] : row;
+  float mean = 0.f, rstd = 1.f;
+  if (norm || l2n) {
+    if (norm) {
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+      mean = warp_sum(s) * (1.0f / (128.0f * NCH));
+    }
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const float d0 = v[k].x - mean, d1 = v[k].y - mean, d2 = v[k].z - mean, d3 = v[k].w - mean;
+      q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+    }
+    q = warp_sum(q);
+    rstd = l2n ? rsqrtf(q) : rsqrtf(q * (1.0f / (128.0f * NCH)) + 1e-5f);
+  }
+  const float* sh = has_mod ? a.shift + (size_t)g * a.mod_ld : nullptr;
+  const float* sc = has_mod ? a.scale + (size_t)g * a.mod_ld : nullptr;
+  const float* gt = has_gate ? a.gate + (size_t)g * a.mod_ld : nullptr;
+  const float* av = has_add ? a.addvec + (size_t)g * a.addvec_ld : nullptr;
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) {
+    const int c = lane * 4 + k * 128;
+    float x[4] = {(v[k].x - mean) * rstd, (v[k].y - mean) * rstd, (v[k].z - mean) * rstd, (v[k].w - mean) * rstd};
+    if (has_gamma) {
+      const float4 gm = ldg4(a.gamma + c), bt = ldg4(a.beta + c);
+      x[0] = fmaf(x[0], gm.x, bt.x), x[1] = fmaf(x[1], gm.y, bt.y), x[2] = fmaf(x[2], gm.z, bt.z), x[3] = fmaf(x[3], gm.w, bt.w);
+    }
+    if (has_mod) {
+      const float4 s4 = ldg4(sc + c), h4 = ldg4(sh + c);
+      x[0] = fmaf(x[0], 1.0f + s4.x, h4.x), x[1] = fmaf(x[1], 1.0f + s4.y, h4.y);
+      x[2] = fmaf(x[2], 1.0f + s4.z, h4.z), x[3] = fmaf(x[3], 1.0f + s4.w, h4.w);
+    }
+    if (RT) {
+      if (a.act != LLB_ACT_NONE) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) x[i] = act_rt(x[i], a.act);
+      }
+    } else if (F & F_GELU) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) x[i] = gelu_fast(x[i]);
+    }
+    if (has_gate) {
+      const float4 g4 = ldg4(gt + c);
+      x[0] *= g4.x, x[1] *= g4.y, x[2] *= g4.z, x[3] *= g4.w;
+    }
+    if (has_resid) {
+      const float4 r4 = (NRES == NCH) ? res[NRES == NCH ? k : 0] : *reinterpret_cast<const float4*>(a.resid + (size_t)row * a.resid_ld + c);
+      x[0] += r4.x, x[1] += r4.y, x[2] += r4.z, x[3] += r4.w;
+    }
+    if (has_add) {
+      const float4 a4 = ldg4(av + c);
+      x[0] += a4.x, x[1] += a4.y, x[2] += a4.z, x[3] += a4.w;
+    }
+    if (out32) {
+      const float4 o = make_float4(x[0], x[1], x[2], x[3]);
+      *reinterpret_cast<float4*>(a.out_f32 + (size_t)row * a.out_f32_ld + c) = o;
+      if (dup) *reinterpret_cast<float4*>(a.out_f32 + (size_t)(row + dup) * a.out_f32_ld + c) = o;
+    }
+    if (out16) {
+      const uint2 o = make_uint2(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]));
+      *reinterpret_cast<uint2*>(a.out_bf16 + (size_t)row * a.out_bf16_ld + c) = o;
+      if (dup) *reinterpret_cast<uint2*>(a.out_bf16 + (size_t)(row + dup) * a.out_bf16_ld + c) = o;
+    }
+  }
+}
+
+template <unsigned F>
+bool launch_reg(int nch, int grid, const RowLnDev& d, cudaStream_t stream) {
+  switch (nch) {
+    case 1: row_ln_reg_kernel<1, F><<<grid, 256, 0, stream>>>(d); return true;
+    case 2: row_ln_reg_kernel<2, F><<<grid, 256, 0, stream>>>(d); return true;
+    case 4: row_ln_reg_kernel<4, F><<<grid, 256, 0, stream>>>(d); return true;
+    case 6: row_ln_reg_kernel<6, F><<<grid, 256, 0, stream>>>(d); return true;
+    case 8: row_ln_reg_kernel<8, F><<<grid, 256, 0, stream>>>(d); return true;
+    case 12: row_ln_reg_kernel<12, F><<<grid, 256, 0, stream>>>(d); return true;
+    case 16: row_ln_reg_kernel<16, F><<<grid, 256, 0, stream>>>(d); return true;
+    case 24: row_ln_reg_kernel<24, F><<<grid, 256, 0, stream>>>(d); return true;
+    case 32: row_ln_reg_kernel<32, F><<<grid, 256, 0, stream>>>(d); return true;
+  }
+  return false;
+}
+
 __global__ void f32_to_bf16_kernel(const float* __restrict__ src, int src_ld, __nv_bfloat16* __restrict__ dst, int dst_ld,
                                    int rows, int cols, int pad_cols) {
   const size_t total = (size_t)rows * pad_cols;
@@ -123,7 +247,12 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(const float* __restrict
   float s = 0.f;
   for (int k = lane; k < in_f; k += 32) s = fmaf(x[k], w[k], s);
   s = warp_sum(s);
-  if (lane == 0) out[(size_t)r * out_ld + o] = act_rt(s + (b ? b[o] : 0.0f), act);
+  if (lane == 0) {
+    float y = s + (b ? b[o] : 0.0f);
+    if (act == LLB_ACT_SILU) y = y / (1.0f + expf(-y));   // accurate form: this feeds the timestep table
+    else y = act_rt(y, act);
+    out[(size_t)r * out_ld + o] = y;
+  }
 }
 
 }  // namespace
@@ -131,10 +260,38 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(const float* __restrict
 int launch_row_ln(const RowLnArgs& a, cudaStream_t stream) {
   if (a.rows <= 0) return LLB_OK;
   LLB_CHECK_ARG(a.width % 4 == 0 && a.in_ld % 4 == 0, "row_ln: width %d / ld %d must be multiples of 4", a.width, a.in_ld);
+  LLB_CHECK_ARG((a.shift == nullptr) == (a.scale == nullptr), "row_ln: shift and scale come together");
   RowLnDev d{a.in, a.in_ld, a.in_bf16 ? 1 : 0, a.rows, a.width, a.normalize ? 1 : 0, a.gamma, a.beta, a.row_group,
              a.shift, a.scale, a.gate, a.mod_ld, a.act, a.resid, a.resid_ld, a.addvec, a.addvec_ld, a.out_f32,
              a.out_f32_ld, a.out_bf16, a.out_bf16_ld, a.dup_rows, a.l2_normalize ? 1 : 0};
-  row_ln_kernel<<<ceil_div(a.rows, 8), 256, 0, stream>>>(d);
+  ProfScope prof(a.prof_slot, stream);
+  const int grid = ceil_div(a.rows, 8);
+  // all vector operands of the register path are read as float4
+  const bool vec_ok = a.mod_ld % 4 == 0 && a.addvec_ld % 4 == 0 && a.resid_ld % 4 == 0 && a.out_f32_ld % 4 == 0 && a.out_bf16_ld % 4 == 0;
+  const int nch = (a.width % 128 == 0 && vec_ok) ? a.width / 128 : 0;
+  unsigned f = 0;
+  f |= a.in_bf16 ? F_IN_BF16 : 0, f |= a.normalize ? F_NORM : 0, f |= a.gamma ? F_GAMMA : 0, f |= a.scale ? F_MOD : 0;
+  f |= a.act == LLB_ACT_GELU ? F_GELU : 0, f |= a.gate ? F_GATE : 0, f |= a.resid ? F_RESID : 0, f |= a.addvec ? F_ADDVEC : 0;
+  f |= a.out_f32 ? F_OUT_F32 : 0, f |= a.out_bf16 ? F_OUT_BF16 : 0;
+  const bool plain = !a.l2_normalize && a.dup_rows == 0 && (a.act == LLB_ACT_NONE || a.act == LLB_ACT_GELU);
+  // hot variants (compile-time masks)
+  constexpr unsigned V_DIT = F_IN_BF16 | F_NORM | F_MOD | F_GATE | F_RESID | F_OUT_F32 | F_OUT_BF16;       // x += g (LN(y)(1+s)+b)
+  constexpr unsigned V_MLP = F_IN_BF16 | F_NORM | F_GAMMA | F_GELU | F_OUT_BF16;                            // GELU(LN_affine(z))
+  constexpr unsigned V_ENC = F_NORM | F_GAMMA | F_GELU | F_RESID | F_ADDVEC | F_OUT_F32 | F_OUT_BF16;       // GIN encoder layer tail
+  constexpr unsigned V_ENC_LAST = F_NORM | F_GAMMA | F_RESID | F_OUT_F32 | F_OUT_BF16;
+  constexpr unsigned V_PRED = F_NORM | F_MOD | F_GELU | F_GATE | F_RESID | F_ADDVEC | F_OUT_F32 | F_OUT_BF16;  // GIN predictor layer tail
+  constexpr unsigned V_PRED_LAST = F_NORM | F_MOD | F_GATE | F_RESID | F_OUT_F32 | F_OUT_BF16;
+  bool done = false;
+  if (nch > 0 && plain) {
+    if (f == V_DIT) done = launch_reg<V_DIT>(nch, grid, d, stream);
+    else if (f == V_MLP) done = launch_reg<V_MLP>(nch, grid, d, stream);
+    else if (f == V_ENC) done = launch_reg<V_ENC>(nch, grid, d, stream);
+    else if (f == V_ENC_LAST) done = launch_reg<V_ENC_LAST>(nch, grid, d, stream);
+    else if (f == V_PRED) done = launch_reg<V_PRED>(nch, grid, d, stream);
+    else if (f == V_PRED_LAST) done = launch_reg<V_PRED_LAST>(nch, grid, d, stream);
+  }
+  if (!done && nch > 0) done = launch_reg<F_RUNTIME>(nch, grid, d, stream);
+  if (!done) row_ln_kernel<<<grid, 256, 0, stream>>>(d);
   LLB_CUDA_OK(cudaGetLastError());
   return LLB_OK;
 }

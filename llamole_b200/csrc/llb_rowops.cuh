@@ -31,6 +31,7 @@ struct RowLnArgs {
   int out_bf16_ld = 0;
   int dup_rows = 0;
   bool l2_normalize = false;  // out = v / ||v|| instead of LN (GraphCLIP head)
+  int prof_slot = LLB_PROF_LN_MOD_RES;
 };
 int launch_row_ln(const RowLnArgs& a, cudaStream_t stream);
 

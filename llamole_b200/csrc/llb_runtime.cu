@@ -3,6 +3,7 @@
 #include <stdarg.h>
 
 #include <mutex>
+#include <vector>
 
 #include "llb_gemm.cuh"
 
@@ -21,6 +22,49 @@ int fail(int code, const char* fmt, ...) {
   g_last_error = buf;
   return code;
 }
+
+// ---- live profiling -------------------------------------------------------------------------------
+namespace {
+struct ProfRec {
+  int slot;
+  cudaEvent_t a, b;
+};
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof_recs;
+std::vector<cudaEvent_t> g_prof_pool;
+double g_prof_ms[LLB_PROF_SLOTS];
+int64_t g_prof_n[LLB_PROF_SLOTS];
+cudaEvent_t prof_event() {
+  if (!g_prof_pool.empty()) {
+    cudaEvent_t e = g_prof_pool.back();
+    g_prof_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+void prof_drain() {
+  for (auto& r : g_prof_recs) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      g_prof_ms[r.slot] += ms;
+      g_prof_n[r.slot] += 1;
+    }
+    g_prof_pool.push_back(r.a);
+    g_prof_pool.push_back(r.b);
+  }
+  g_prof_recs.clear();
+}
+}  // namespace
+
+bool profile_on() { return g_prof_on; }
+void profile_begin(int slot, cudaStream_t s) {
+  ProfRec r{slot, prof_event(), prof_event()};
+  cudaEventRecord(r.a, s);
+  g_prof_recs.push_back(r);
+}
+void profile_end(cudaStream_t s) { cudaEventRecord(g_prof_recs.back().b, s); }
 
 int num_sms() {
   static int sms = 0;
@@ -66,19 +110,21 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-int make_tensor_map_bf16(CUtensorMap* out, const void* ptr, int rows, int cols, int ld_elems, int box_rows) {
+int make_tensor_map_2d(CUtensorMap* out, const void* ptr, int elem_bytes, int rows, int cols, int ld_elems, int box_cols,
+                       int box_rows, int swizzle_bytes) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(LLB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld_elems * 2};
-  cuuint32_t box[2] = {(cuuint32_t)GEMM_BK, (cuuint32_t)box_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld_elems * elem_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = fn(out, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
-    return fail(LLB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for rows=%d cols=%d ld=%d box_rows=%d ptr=%p", (int)r, rows,
-                cols, ld_elems, box_rows, ptr);
+    return fail(LLB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for rows=%d cols=%d ld=%d elem=%d box=%dx%d ptr=%p", (int)r, rows,
+                cols, ld_elems, elem_bytes, box_cols, box_rows, ptr);
   return LLB_OK;
 }
 
@@ -104,11 +150,12 @@ static int pick_bn(int M, int N) {
 template <int ACT, bool F32>
 static int gemm_dispatch_bn(const void* A, int lda, const void* W, int ldw, const float* bias, void* C, int ldc, int M,
                             int N, int K, cudaStream_t stream, GemmCounters* ctr) {
-  EpiBiasAct<ACT, F32> epi{C, bias, ldc};
+  LLB_CHECK_ARG(bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0, "gemm: bias must be 16-byte aligned");
+  EpiBiasAct<ACT, F32> epi{C, ldc, bias};
   switch (pick_bn(M, N)) {
-    case 256: return launch_gemm<256, 8>(A, lda, W, ldw, M, N, K, epi, stream, ctr);
-    case 128: return launch_gemm<128, 8>(A, lda, W, ldw, M, N, K, epi, stream, ctr);
-    default: return launch_gemm<64, 8>(A, lda, W, ldw, M, N, K, epi, stream, ctr);
+    case 256: return launch_gemm<256>(A, lda, W, ldw, M, N, K, epi, stream, ctr);
+    case 128: return launch_gemm<128>(A, lda, W, ldw, M, N, K, epi, stream, ctr);
+    default: return launch_gemm<64>(A, lda, W, ldw, M, N, K, epi, stream, ctr);
   }
 }
 
@@ -138,6 +185,31 @@ extern "C" {
 const char* llb_last_error(void) { return llb::g_last_error.c_str(); }
 
 int llb_version(void) { return 100; }
+
+int llb_profile_enable(int on) {
+  llb::prof_drain();
+  llb::g_prof_on = on != 0;
+  for (int i = 0; i < LLB_PROF_SLOTS; ++i) llb::g_prof_ms[i] = 0.0, llb::g_prof_n[i] = 0;
+  return LLB_OK;
+}
+
+int llb_profile_read(int slot, double* total_ms, int64_t* launches) {
+  LLB_CHECK_ARG(slot >= 0 && slot < LLB_PROF_SLOTS && total_ms && launches, "llb_profile_read: bad argument");
+  llb::prof_drain();
+  *total_ms = llb::g_prof_ms[slot];
+  *launches = llb::g_prof_n[slot];
+  llb::g_prof_ms[slot] = 0.0;
+  llb::g_prof_n[slot] = 0;
+  return LLB_OK;
+}
+
+const char* llb_profile_slot_name(int slot) {
+  static const char* names[LLB_PROF_SLOTS] = {
+      "gemm_qkv", "gemm_proj", "gemm_fc1", "gemm_fc2", "gemm_adaln", "gemm_other", "attention", "ln_mod_res", "dit_step",
+      "dit_misc", "gin_aggregate", "gin_pool", "gin_gemm_mlp0", "gin_gemm_mlp4", "gin_rowln", "gin_misc", "gin_gemm_head",
+      "gin_topk"};
+  return (slot >= 0 && slot < LLB_PROF_SLOTS) ? names[slot] : "?";
+}
 
 int llb_arch_check(int device) {
   int major = 0, minor = 0;
