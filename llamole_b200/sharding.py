@@ -1,0 +1,97 @@
+"""Multi-GPU use of the hot path: independent molecules / graphs are sharded over the ranks of one node and the
+results are exchanged with ONE all-gather at the end.  There is no data-path collective:
+weights are replicated, every unit of work is independent, and the counter RNG is keyed by the GLOBAL molecule
+index so the sampled graphs do not depend on the number of GPUs.
+
+One process per GPU (torchrun); `torch.distributed` is plumbing only (NCCL on GPUs, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous slice [start, stop) of `total` units for `rank`; sizes differ by at most one."""
+    base, rem = divmod(total, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def balanced_graph_ranges(nodes_per_graph: Sequence[int], world: int) -> List[Tuple[int, int]]:
+    """Contiguous graph ranges with (nearly) equal node counts: GIN cost is proportional to nodes, and contiguous
+    ranges keep every rank's CSR segments contiguous."""
+    counts = torch.as_tensor(nodes_per_graph, dtype=torch.int64)
+    G = int(counts.numel())
+    prefix = torch.cumsum(counts, 0)
+    total = int(prefix[-1]) if G else 0
+    bounds = [0]
+    for r in range(1, world):
+        target = total * r / world
+        cut = int(torch.searchsorted(prefix, torch.tensor(target, dtype=prefix.dtype)).item())
+        bounds.append(min(max(cut, bounds[-1]), G))
+    bounds.append(G)
+    return [(bounds[i], bounds[i + 1]) for i in range(world)]
+
+
+def split_graph_batch(x, edge_index, edge_attr, batch, g0: int, g1: int):
+    """Sub-batch of graphs [g0, g1) of a PyG-style batch (batch sorted ascending, edges never cross graphs)."""
+    node_sel = (batch >= g0) & (batch < g1)
+    idx = node_sel.nonzero().squeeze(1)
+    if idx.numel() == 0:
+        z = x.new_zeros((0,))
+        return z, edge_index.new_zeros((2, 0)), edge_attr.new_zeros((0,)), batch.new_zeros((0,))
+    n0 = int(idx[0])
+    e_sel = node_sel[edge_index[1]]
+    return x[idx], edge_index[:, e_sel] - n0, edge_attr[e_sel], batch[idx] - g0
+
+
+def all_gather_rows(t: torch.Tensor, group=None) -> torch.Tensor:
+    """All-gather along dim 0 for per-rank tensors whose first dimension may differ (pads to the max)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return t
+    world = dist.get_world_size(group)
+    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    m = max(sizes)
+    pad = t.new_zeros((m,) + tuple(t.shape[1:]))
+    pad[: t.shape[0]] = t
+    outs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(outs, pad, group=group)
+    return torch.cat([o[:s] for o, s in zip(outs, sizes)], dim=0)
+
+
+def sample_graphs_sharded(generate_fn: Callable, properties: torch.Tensor, text_embedding: torch.Tensor, n_nodes: torch.Tensor,
+                          seed: int = 0, group=None, **kw):
+    """Shard a sampling batch over the ranks and gather the integer graphs.
+
+    generate_fn(properties, text_embedding, n_nodes=..., seed=..., mol_index_base=...) -> (X, E, n) as
+    GraphDiT.generate_graphs.  Every rank passes the FULL batch and receives the FULL result.
+    """
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    s, e = shard_range(properties.shape[0], rank, world)
+    X, E, n = generate_fn(properties[s:e], text_embedding[s:e], n_nodes=n_nodes[s:e], seed=seed, mol_index_base=s, **kw)
+    return all_gather_rows(X, group), all_gather_rows(E, group), all_gather_rows(n, group)
+
+
+def encode_graphs_sharded(forward_fn: Callable, x, edge_index, edge_attr, batch, num_graphs: Optional[int] = None, group=None,
+                          extra: Optional[torch.Tensor] = None):
+    """Shard a graph batch by node count, run forward_fn(x, edge_index, edge_attr, batch[, extra_rows]) on the local
+    range and gather the per-graph rows (embeddings, logits or top-k) from all ranks."""
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    G = int(batch[-1].item()) + 1 if num_graphs is None else num_graphs
+    counts = torch.bincount(batch, minlength=G)
+    g0, g1 = balanced_graph_ranges(counts.tolist(), world)[rank]
+    sub = split_graph_batch(x, edge_index, edge_attr, batch, g0, g1)
+    if g1 > g0:
+        out = forward_fn(*sub, extra[g0:g1]) if extra is not None else forward_fn(*sub)
+    else:
+        probe = forward_fn(*split_graph_batch(x, edge_index, edge_attr, batch, 0, 1), *([extra[0:1]] if extra is not None else []))
+        out = probe[:0]
+    return all_gather_rows(out, group)
