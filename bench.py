@@ -49,6 +49,15 @@ def peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
 
 
+def ncu_traffic(slot):
+    """DRAM bytes per launch of a kernel from the committed `ncu --set full` capture (profiles/traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p))["bytes_per_launch"].get(slot)
+    except Exception:
+        return None
+
+
 def dit_flops_per_pass(n_nodes, H=1024, D=28, d0=266):
     """Algorithmic FLOPs of one denoiser pass over molecules with n valid atoms each."""
     n = n_nodes.double()
@@ -242,6 +251,8 @@ def main():
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and not os.environ.get("LLB_KEEP_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=device)
 
     def barrier():
@@ -309,7 +320,7 @@ def main():
         dur = prof[dom][0] / prof[dom][1] / 1e3
         ach = gemm_flops[dom] / dur / 1e12
         roofline = {"bound": "tensor", "kernel": f"gemm_tcgen05_kernel ({dom})", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                    "frac": ach / pk["tf_sustained"], "traffic": None, "peak_source": pk["source"] + " (sustained: timed inside a long step)",
+                    "frac": ach / pk["tf_sustained"], "traffic": ncu_traffic(dom), "peak_source": pk["source"] + " (sustained: timed inside a long step)",
                     "launch_ms": dur * 1e3, "flops_per_launch": gemm_flops[dom],
                     "whole_step": {"flops_per_step": flops_step, "achieved": flops_step / (ms_step / 1e3) / 1e12, "frac": step_frac}}
     # ------------------------------------------------------------------ e2e through the public API (host buffers)
@@ -412,7 +423,7 @@ def bench_gin(args, device, rank, world, barrier, max_over_ranks, pk):
         "config": {"hidden": H, "layers": L, "timed": "CSR build (llb_gin_bind) + GraphCLIP forward, inputs resident in HBM"},
         "e2e": {"value": world * G / (e2e_ms / 1e3), "unit": "graphs/s", "h2d_bytes_per_step": (n * 2 + e * 3) * 8, "d2h_bytes_per_step": G * H * 4},
         "roofline": {"bound": "hbm", "kernel": "gin_aggregate_kernel", "achieved": agg_bytes / (agg_ms / 1e3) / 1e9, "peak": pk["hbm"],
-                     "unit": "GB/s", "frac": agg_bytes / (agg_ms / 1e3) / 1e9 / pk["hbm"], "traffic": None, "launch_ms": agg_ms,
+                     "unit": "GB/s", "frac": agg_bytes / (agg_ms / 1e3) / 1e9 / pk["hbm"], "traffic": ncu_traffic("gin_aggregate"), "launch_ms": agg_ms,
                      "bytes_per_launch": agg_bytes, "peak_source": pk["source"]},
         "mlp_gemms": {"tflops": mlp_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms else None, "frac_of_sustained": mlp_flops / (gemm_ms / 1e3) / 1e12 / pk["tf_sustained"] if gemm_ms else None,
                       "ms_per_forward": gemm_ms},

@@ -23,14 +23,14 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_EPI_WARPS = 8;
 constexpr int GEMM_THREADS = 32 * (GEMM_EPI_WARPS + 4);
-constexpr int GEMM_STAGING_PER_WARP = 4096;  // 32 rows x 128 B (or 2 x 32 rows x 64 B)
+constexpr int GEMM_STAGING_PER_WARP = 8192;  // ring of 32-row staging boxes: 4 x (32 x 64 B) or 2 x (32 x 128 B)
 
 template <int BN>
 struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = (BN == 256) ? 3 : (BN == 128 ? 5 : 6);
   static constexpr int TMEM_COLS = 2 * BN;  // 512 / 256 / 128
   static constexpr int STAGING_BYTES = GEMM_EPI_WARPS * GEMM_STAGING_PER_WARP;
   static constexpr int BAR_BYTES = 256;
@@ -50,6 +50,83 @@ __device__ __forceinline__ void bulk_wait_read() {
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+#ifdef LLB_GEMM_TRACE
+// Debug-only instrumentation (tools/gemm_trace.cu, never compiled into the library): per-tile cycle stamps of every
+// role of CTA pair 0, and an experiment mask that switches single pipeline stages off to find the binding one
+// (1 = no MMA issue, 2 = no epilogue at all, 4 = no epilogue math, 8 = no epilogue store).
+__device__ long long* g_gemm_trace = nullptr;   // [tile][16]
+__device__ int g_gemm_exp = 0;
+#define LLB_TRACE(tile_idx, slot, value) \
+  do { if (g_gemm_trace && blockIdx.x < 2) g_gemm_trace[((size_t)(tile_idx) * 2 + blockIdx.x) * 16 + (slot)] = (value); } while (0)
+#define LLB_EXP(bit) ((g_gemm_exp & (bit)) != 0)
+#else
+#define LLB_TRACE(tile_idx, slot, value) do { } while (0)
+#define LLB_EXP(bit) false
+#endif
+
+// One epilogue warp's share of a 128 x BN accumulator tile: warp % 4 selects the TMEM lane quarter (32 rows), the
+// warps sharing a quarter split the columns.  tcgen05.ld -> fused functor -> swizzled smem staging -> TMA store.
+template <int BN, bool TMA_STORE, class Epi>
+__device__ __forceinline__ void gemm_epilogue_tile(const Epi& epi, const CUtensorMap* tmC, uint32_t tmem_acc, int m0, int n0, int M,
+                                                   int N, uint8_t* stg, int& buf) {
+  constexpr int ELEM = Epi::OUT_F32 ? 4 : 2;
+  constexpr int ROW_BYTES = Epi::CHUNK * ELEM;
+  constexpr int NBUF = GEMM_STAGING_PER_WARP / (32 * ROW_BYTES);
+  constexpr int COLS_PER_WARP = BN / (GEMM_EPI_WARPS / 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int quarter = warp & 3, cg = warp >> 2;
+  const int row = m0 + quarter * 32 + lane;
+  const uint32_t t_row = tmem_acc + ((uint32_t)(quarter * 32) << 16) + cg * COLS_PER_WARP;
+  float v[Epi::CHUNK];
+#pragma unroll 1
+  for (int c = 0; c < COLS_PER_WARP; c += Epi::CHUNK) {
+    const int col0 = n0 + cg * COLS_PER_WARP + c;
+    if (col0 >= N) break;   // warp-uniform
+    tmem_ld32(t_row + c, v);
+    if (Epi::CHUNK == 64) tmem_ld32(t_row + c + 32, v + 32);
+    tmem_ld_wait();
+    if (!LLB_EXP(4)) epi.transform(row, col0, v, M, N);
+    if (LLB_EXP(8)) continue;
+    if (TMA_STORE) {
+      uint8_t* dst = stg + buf * (32 * ROW_BYTES);
+      if (lane == 0) bulk_wait_read<NBUF - 1>();   // the buffer about to be overwritten has been read out
+      __syncwarp();
+      // row `lane` of the staging tile, 16-byte pieces XOR-swizzled exactly like the C tensor map
+      uint8_t* rowp = dst + lane * ROW_BYTES;
+      const int sw = ROW_BYTES == 128 ? (lane & 7) : ((lane >> 1) & 3);
+#pragma unroll
+      for (int p = 0; p < ROW_BYTES / 16; ++p) {
+        uint4 q;
+        if (Epi::OUT_F32) {
+          q = make_uint4(__float_as_uint(v[4 * p]), __float_as_uint(v[4 * p + 1]), __float_as_uint(v[4 * p + 2]),
+                         __float_as_uint(v[4 * p + 3]));
+        } else {
+          q = make_uint4(pack_bf16x2(v[8 * p], v[8 * p + 1]), pack_bf16x2(v[8 * p + 2], v[8 * p + 3]),
+                         pack_bf16x2(v[8 * p + 4], v[8 * p + 5]), pack_bf16x2(v[8 * p + 6], v[8 * p + 7]));
+        }
+        *reinterpret_cast<uint4*>(rowp + ((p ^ sw) << 4)) = q;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(tmC, dst, col0, m0 + quarter * 32);
+        bulk_commit();
+      }
+      buf = (buf + 1) % NBUF;
+    } else if (row < M) {
+      if (Epi::OUT_F32) {
+        float* out = reinterpret_cast<float*>(epi.C) + (size_t)row * epi.ldc + col0;
+        for (int i = 0; i < Epi::CHUNK; ++i)
+          if (col0 + i < N) out[i] = v[i];
+      } else {
+        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(epi.C) + (size_t)row * epi.ldc + col0;
+        for (int i = 0; i < Epi::CHUNK; ++i)
+          if (col0 + i < N) out[i] = __float2bfloat16(v[i]);
+      }
+    }
+  }
+}
+
 // Epilogue functor contract:
 //   static constexpr int  CHUNK   (32 or 64): consecutive accumulator columns handed over per call
 //   static constexpr bool OUT_F32 : element type of C (fp32 or bf16); CHUNK * sizeof(elem) <= 128
@@ -65,7 +142,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   constexpr int ELEM = Epi::OUT_F32 ? 4 : 2;
   constexpr int ROW_BYTES = Epi::CHUNK * ELEM;            // 64 or 128
   static_assert(ROW_BYTES == 64 || ROW_BYTES == 128, "epilogue chunk must be 64 or 128 bytes per row");
-  constexpr int NBUF = GEMM_STAGING_PER_WARP / (32 * ROW_BYTES);  // 2 or 1 staging buffers per warp
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smA = smem;
@@ -162,9 +238,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp < GEMM_EPI_WARPS) {
     // ---------------- epilogue ----------------
-    const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
-    constexpr int COLS_PER_WARP = BN / (GEMM_EPI_WARPS / 4);
-    const int cg = warp >> 2;                        // warps sharing a quarter split the columns
     uint8_t* stg = smStage + warp * GEMM_STAGING_PER_WARP;
     int buf = 0;
     int acc = 0;
@@ -174,55 +247,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int n0 = (tile % num_n) * BN;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int row = m0 + quarter * 32 + lane;
-      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + cg * COLS_PER_WARP;
-      float v[Epi::CHUNK];
-#pragma unroll 1
-      for (int c = 0; c < COLS_PER_WARP; c += Epi::CHUNK) {
-        const int col0 = n0 + cg * COLS_PER_WARP + c;
-        if (col0 >= N) break;   // warp-uniform
-        tmem_ld32(t_row + c, v);
-        if (Epi::CHUNK == 64) tmem_ld32(t_row + c + 32, v + 32);
-        tmem_ld_wait();
-        epi.transform(row, col0, v, M, N);
-        if (TMA_STORE) {
-          uint8_t* dst = stg + buf * (32 * ROW_BYTES);
-          if (lane == 0) bulk_wait_read<NBUF - 1>();   // the buffer about to be overwritten has been read out
-          __syncwarp();
-          // row `lane` of the staging tile, 16-byte pieces XOR-swizzled exactly like the C tensor map
-          uint8_t* rowp = dst + lane * ROW_BYTES;
-          const int sw = ROW_BYTES == 128 ? (lane & 7) : ((lane >> 1) & 3);
-#pragma unroll
-          for (int p = 0; p < ROW_BYTES / 16; ++p) {
-            uint4 q;
-            if (Epi::OUT_F32) {
-              q = make_uint4(__float_as_uint(v[4 * p]), __float_as_uint(v[4 * p + 1]), __float_as_uint(v[4 * p + 2]),
-                             __float_as_uint(v[4 * p + 3]));
-            } else {
-              q = make_uint4(pack_bf16x2(v[8 * p], v[8 * p + 1]), pack_bf16x2(v[8 * p + 2], v[8 * p + 3]),
-                             pack_bf16x2(v[8 * p + 4], v[8 * p + 5]), pack_bf16x2(v[8 * p + 6], v[8 * p + 7]));
-            }
-            *reinterpret_cast<uint4*>(rowp + ((p ^ sw) << 4)) = q;
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tmC, dst, col0, m0 + quarter * 32);
-            bulk_commit();
-          }
-          buf = (buf + 1) % NBUF;
-        } else if (row < M) {
-          if (Epi::OUT_F32) {
-            float* out = reinterpret_cast<float*>(epi.C) + (size_t)row * epi.ldc + col0;
-            for (int i = 0; i < Epi::CHUNK; ++i)
-              if (col0 + i < N) out[i] = v[i];
-          } else {
-            __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(epi.C) + (size_t)row * epi.ldc + col0;
-            for (int i = 0; i < Epi::CHUNK; ++i)
-              if (col0 + i < N) out[i] = __float2bfloat16(v[i]);
-          }
-        }
-      }
+      gemm_epilogue_tile<BN, TMA_STORE>(epi, &tmC, tmem_base + acc * BN, m0, n0, M, N, stg, buf);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -242,12 +267,234 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------------
+// cta_group::2 variant: a CTA PAIR (cluster of 2, same TPC) computes a 256 x 256 tile.  CTA r owns rows
+// [m0 + 128 r, +128) and loads only HALF of the W tile (rows n0 + 128 r ..); tcgen05.mma.cta_group::2 (issued by the
+// leader CTA's single thread) makes both tensor cores read the concatenated B operand, so per SM the shared-memory
+// and L2->SM traffic per MMA drops by a third (A 16 KB + B 16 KB per 64-wide k-block instead of 16 + 32) and the
+// ring deepens to 6 stages.  Barriers: full[] lives in the leader (both CTAs' TMA loads complete_tx on it),
+// empty[] / tmem_full[] are signalled in both CTAs by a multicast tcgen05.commit, tmem_empty[] lives in the leader and
+// collects the epilogue warps of both CTAs.
+// ------------------------------------------------------------------------------------------------
+
+struct Gemm2Cfg {
+  static constexpr int BN = 256;
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;        // 16 KB
+  static constexpr int B_BYTES = (BN / 2) * GEMM_BK * 2;       // 16 KB (this CTA's half of the W tile)
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = 5;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int STAGING_BYTES = GEMM_EPI_WARPS * GEMM_STAGING_PER_WARP;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 256 + 1024;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose completion bytes are credited to the LEADER CTA's mbarrier (peer bit of the cluster address cleared).
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// Arrives (once the issued MMAs have completed) on the barrier at this offset in BOTH CTAs of the pair.
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+
+template <bool TMA_STORE, class Epi>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const __grid_constant__ CUtensorMap tmC, int M, int N, int K, Epi epi) {
+  using Cfg = Gemm2Cfg;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int BN = Cfg::BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smA = smem;
+  uint8_t* smB = smem + STAGES * Cfg::A_BYTES;
+  uint8_t* smStage = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smStage + Cfg::STAGING_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tmem_full = bars + 2 * STAGES;
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int num_m = (M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+  const int num_n = (N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
+
+  if (warp == GEMM_EPI_WARPS && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (TMA_STORE) tma_prefetch_desc(&tmC);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 2 * GEMM_EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  cluster_sync_all();
+  if (warp == GEMM_EPI_WARPS + 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == GEMM_EPI_WARPS) {
+    // ---------------- TMA producer (both CTAs; completion bytes go to the leader's full[]) ----------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int tcount = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++tcount) {
+        const int m0 = (tile / num_n) * (2 * GEMM_BM) + rank * GEMM_BM;
+        const int n0 = (tile % num_n) * BN + rank * (BN / 2);
+        long long wsum = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+#ifdef LLB_GEMM_TRACE
+          const long long w0 = clock64();
+#endif
+          mbar_wait(&empty[stage], phase ^ 1);
+#ifdef LLB_GEMM_TRACE
+          wsum += clock64() - w0;
+          if (kb == num_kb - 1) { LLB_TRACE(tcount, 0, wsum); LLB_TRACE(tcount, 1, clock64()); }
+#endif
+          if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
+          tma_load_2d_2sm(smA + stage * Cfg::A_BYTES, &tmA, &full[stage], kb * GEMM_BK, m0);
+          tma_load_2d_2sm(smB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * GEMM_BK, n0);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == GEMM_EPI_WARPS + 1) {
+    // ---------------- MMA issuer (leader CTA only) ----------------
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * GEMM_BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      int tcount = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++tcount) {
+        LLB_TRACE(tcount, 2, clock64());
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        LLB_TRACE(tcount, 3, clock64());
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        long long fsum = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+#ifdef LLB_GEMM_TRACE
+          const long long w0 = clock64();
+#endif
+          mbar_wait(&full[stage], phase);
+#ifdef LLB_GEMM_TRACE
+          fsum += clock64() - w0;
+          if (kb == num_kb - 1) { LLB_TRACE(tcount, 4, fsum); LLB_TRACE(tcount, 5, clock64()); }
+#endif
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smA + stage * Cfg::A_BYTES);
+          const uint32_t b_addr = smem_u32(smB + stage * Cfg::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            if (!LLB_EXP(1))
+              umma_bf16_2sm(d_tmem, umma_desc_k128(a_addr + k * 32), umma_desc_k128(b_addr + k * 32), idesc,
+                            (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_2sm(&empty[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_2sm(&tmem_full[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp < GEMM_EPI_WARPS) {
+    // ---------------- epilogue (each CTA drains its own 128 x 256 half) ----------------
+    uint8_t* stg = smStage + warp * GEMM_STAGING_PER_WARP;
+    int buf = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int tcount = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++tcount) {
+      const int m0 = (tile / num_n) * (2 * GEMM_BM) + rank * GEMM_BM;
+      const int n0 = (tile % num_n) * BN;
+      if (warp == 0 && lane == 0) LLB_TRACE(tcount, 6, clock64());
+      mbar_wait(&tmem_full[acc], acc_phase);
+      if (warp == 0 && lane == 0) LLB_TRACE(tcount, 7, clock64());
+      tc_fence_after();
+      if (!LLB_EXP(2)) gemm_epilogue_tile<BN, TMA_STORE>(epi, &tmC, tmem_base + acc * BN, m0, n0, M, N, stg, buf);
+      tc_fence_before();
+      __syncwarp();
+      if (warp == 0 && lane == 0) LLB_TRACE(tcount, 8, clock64());
+      if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+    if (TMA_STORE && lane == 0) bulk_wait_all();
+  }
+  tc_fence_before();
+  cluster_sync_all();   // nobody leaves while the peer may still signal its barriers / read its operand half
+  if (warp == GEMM_EPI_WARPS + 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------------
 // 2-D tensor map: inner dim = cols (contiguous), outer dim = rows; box = box_cols x box_rows;
 // swizzle_bytes in {64, 128} must equal box_cols * elem_bytes.
 int make_tensor_map_2d(CUtensorMap* out, const void* ptr, int elem_bytes, int rows, int cols, int ld_elems, int box_cols,
                        int box_rows, int swizzle_bytes);
+
+bool gemm_pair_enabled();   // LLB_GEMM_PAIR=0 forces the single-CTA kernel (debug / A-B comparison)
 
 struct GemmCounters {
   int64_t launches = 0;
@@ -271,18 +518,38 @@ int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, in
   else tmC = tmA;
   const int tiles = ceil_div(M, GEMM_BM) * ceil_div(N, BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  static bool configured[2] = {false, false};  // per template instantiation
-  auto launch = [&](auto kern, int which) -> int {
-    if (!configured[which]) {
-      LLB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-      configured[which] = true;
-    }
-    ProfScope prof(ctr ? ctr->slot : LLB_PROF_GEMM_OTHER, stream);
-    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, M, N, K, epi);
-    return LLB_OK;
-  };
-  if (tma_store) LLB_TRY(launch(gemm_tcgen05_kernel<BN, true, Epi>, 0));
-  else LLB_TRY(launch(gemm_tcgen05_kernel<BN, false, Epi>, 1));
+  static bool configured[4] = {false, false, false, false};  // per template instantiation
+  // CTA-pair kernel: wide problems whose 256 x 256 pair-tiles fill the machine
+  const int pair_tiles = ceil_div(M, 2 * GEMM_BM) * ceil_div(N, 256);
+  const bool use_pair = BN == 256 && gemm_pair_enabled() && pair_tiles >= num_sms() / 2;
+  if (use_pair) {
+    CUtensorMap tmBh;
+    LLB_TRY(make_tensor_map_2d(&tmBh, W, 2, N, K, ldw, GEMM_BK, 128, 128));
+    auto launch2 = [&](auto kern, int which) -> int {
+      if (!configured[which]) {
+        LLB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::SMEM_BYTES));
+        configured[which] = true;
+      }
+      const int pairs = pair_tiles < num_sms() / 2 ? pair_tiles : num_sms() / 2;
+      ProfScope prof(ctr ? ctr->slot : LLB_PROF_GEMM_OTHER, stream);
+      kern<<<2 * pairs, GEMM_THREADS, Gemm2Cfg::SMEM_BYTES, stream>>>(tmA, tmBh, tmC, M, N, K, epi);
+      return LLB_OK;
+    };
+    if (tma_store) LLB_TRY(launch2(gemm_tcgen05_2cta_kernel<true, Epi>, 2));
+    else LLB_TRY(launch2(gemm_tcgen05_2cta_kernel<false, Epi>, 3));
+  } else {
+    auto launch = [&](auto kern, int which) -> int {
+      if (!configured[which]) {
+        LLB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        configured[which] = true;
+      }
+      ProfScope prof(ctr ? ctr->slot : LLB_PROF_GEMM_OTHER, stream);
+      kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, M, N, K, epi);
+      return LLB_OK;
+    };
+    if (tma_store) LLB_TRY(launch(gemm_tcgen05_kernel<BN, true, Epi>, 0));
+    else LLB_TRY(launch(gemm_tcgen05_kernel<BN, false, Epi>, 1));
+  }
   LLB_CUDA_OK(cudaGetLastError());
   if (ctr) ctr->launches++;
   return LLB_OK;

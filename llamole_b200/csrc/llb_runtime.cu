@@ -1,6 +1,7 @@
 // Runtime plumbing of the C ABI: status/last-error, architecture gate, TMA descriptor encoding, and the
 // runtime-dispatched GEMM entry (llb_gemm_bf16).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <mutex>
 #include <vector>
@@ -65,6 +66,15 @@ void profile_begin(int slot, cudaStream_t s) {
   g_prof_recs.push_back(r);
 }
 void profile_end(cudaStream_t s) { cudaEventRecord(g_prof_recs.back().b, s); }
+
+bool gemm_pair_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("LLB_GEMM_PAIR");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
 
 int num_sms() {
   static int sms = 0;

@@ -1,5 +1,5 @@
 import json, sys
-d = json.load(open(sys.argv[1]))
+d = json.loads([l for l in open(sys.argv[1]).read().splitlines() if l.startswith("{")][-1])
 r = d["roofline"]
 print("ms/step %.2f  mol/s %.2f  step_frac %.3f  dom %s frac %.3f  e2e %.2f" % (d["ms_per_step"], d["value"], r["whole_step"]["frac"], r["kernel"], r["frac"], d["e2e"]["value"]))
 print("  " + "  ".join("%s=%.2f" % (k, v["ms_per_step"]) for k, v in d["kernel_breakdown"].items()))
