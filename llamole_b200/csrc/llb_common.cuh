@@ -77,29 +77,25 @@ struct Arena {
 // Device math
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
-// GELU with erf from Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7, i.e. below fp32 round-off of the surrounding
-// arithmetic): 2 MUFU + ~12 FMA-pipe instructions instead of erff's ~35, which made the fc1 epilogue issue-bound.
-__device__ __forceinline__ float rcp_approx(float x) {
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
+// Exact-erf GELU restated as gelu(x) = max(x, 0) - |x| * Phi(-|x|) with Phi(-a) = 2^P(a), P a degree-5 minimax fit
+// of log2(Phi(-a)) on [0, 6] (leading coefficient negative, so P -> -inf and the correction -> 0 beyond the fit range).
+// Max |error| against the fp64 erf form is 6.4e-7 over [-8, 8] (tools/fit_gelu.py), i.e. fp32 round-off of the
+// surrounding arithmetic, for 6 FFMA + 1 FMNMX + 1 MUFU.EX2 per element -- erff costs ~35 instructions, the previous
+// Abramowitz-Stegun form 16 + 2 MUFU, and both made the fc1 epilogue slow the tensor pipe down.
 __device__ __forceinline__ float ex2_approx(float x) {
   float r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
 __device__ __forceinline__ float gelu_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(t, 1.061405429f, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float e = ex2_approx(x * x * -0.72134752044448170f);   // exp(-z^2) = 2^(-x^2 log2(e) / 2)
-  const float erf_abs = fmaf(-p * t, e, 1.0f);
-  const float hx = 0.5f * x;
-  return fmaf(hx, copysignf(erf_abs, x), hx);
+  const float a = fabsf(x);
+  float p = -0.0004733077904837858f;
+  p = fmaf(p, a, 0.007084582472665392f);
+  p = fmaf(p, a, -0.05182752433176751f);
+  p = fmaf(p, a, -0.45999221096226367f);
+  p = fmaf(p, a, -1.150787981711536f);
+  p = fmaf(p, a, -1.0000376025053335f);
+  return fmaf(-a, ex2_approx(p), fmaxf(x, 0.0f));
 }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 __device__ __forceinline__ float softsign(float x) { return x / (1.0f + fabsf(x)); }
