@@ -67,6 +67,16 @@ const char* llb_profile_slot_name(int slot);
 int llb_gemm_bf16(const void* A, int lda, const void* W, int ldw, const float* bias, void* C, int ldc, int M,
                   int N, int K, int act, int out_fp32, llb_stream_t stream);
 
+/* Fused tail of a GraphDiT block half (transformer.py:143-144):
+ *   x[r,:] += gate[g] * ( LayerNorm(A[r,:] . W^T + bias) * (1 + scale[g]) + shift[g] ),  g = row_group[r]
+ * LayerNorm over the N output columns (eps 1e-5, no affine) on the fp32 accumulators; x (M, ldx) fp32 is updated
+ * in place and xb (M, ldxb) receives its bf16 copy (the next GEMM's operand; must not alias A).  shift / scale /
+ * gate point at (groups, mod_ld) fp32 matrices.  N must be 256, 512, 768 or 1024 (one CTA per 256 columns, one
+ * thread-block cluster per 128-row tile); other widths return LLB_ERR_INVALID. */
+int llb_gemm_ln_residual(const void* A, int lda, const void* W, int ldw, const float* bias, const int32_t* row_group,
+                         const float* shift, const float* scale, const float* gate, int mod_ld, float* x, int ldx,
+                         void* xb, int ldxb, int M, int N, int K, llb_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------
  * GraphDiT sampler  (graph_decoder/diffusion_model.py:252-399, transformer.py:93-187, layers.py:56-116,
  * conditions.py:19-123, diffusion_utils.py:93-108,316-349,376-413,476-518)

@@ -6,6 +6,7 @@
 
 #include "llb_dit_kernels.cuh"
 #include "llb_gemm.cuh"
+#include "llb_gemm_ln.cuh"
 #include "llb_rowops.cuh"
 
 namespace llb {
@@ -295,6 +296,10 @@ static int dit_forward(llb_dit* h, int t, cudaStream_t s) {
                         B + 1, 2 * L.d0, H, LLB_ACT_NONE, true, s, ctr));
   // 3. transformer blocks
   const float q_scale = 1.4426950408889634f / sqrtf((float)DIT_DH);
+  const bool fused_ln = gemm_ln_supported(H, H) && gemm_ln_supported(H, F) && gemm_ln_enabled();
+  // With K = 4 H the GEMM main loop dominates and the CTA-pair kernel's is faster than the cluster kernel's, which more
+  // than pays for the separate row kernel; LLB_FUSED_LN=2 fuses fc2 as well (A/B comparison).
+  const bool fused_fc2 = gemm_ln_mode() == 2;
   for (int l = 0; l < D; ++l) {
     const float* mod = h->mod + (size_t)l * (B + 1) * 6 * H;
     ctr->slot = LLB_PROF_GEMM_QKV;
@@ -306,22 +311,34 @@ static int dit_forward(llb_dit* h, int t, cudaStream_t s) {
     }
     LLB_CUDA_OK(cudaGetLastError());
     h->launches++;
-    ctr->slot = LLB_PROF_GEMM_PROJ;
-    LLB_TRY(gemm_bias_act(h->attn, H, h->w<void>(L.proj_w[l]), H, h->w<float>(L.proj_b[l]), h->y, H, M, H, H, LLB_ACT_NONE, false, s, ctr));
+    // x += gate * (LN(linear(.)) (1 + scale) + shift): fused into the GEMM epilogue when a cluster can hold a full row
     RowLnArgs a;
     a.in = h->y, a.in_ld = H, a.in_bf16 = true, a.rows = M, a.width = H;
     a.row_group = h->row_group, a.mod_ld = 6 * H;
-    a.shift = mod, a.scale = mod + H, a.gate = mod + 2 * H;
     a.resid = h->x, a.resid_ld = H, a.out_f32 = h->x, a.out_f32_ld = H, a.out_bf16 = h->xb, a.out_bf16_ld = H;
-    LLB_TRY(launch_row_ln(a, s));
-    h->launches++;
+    GemmLnArgs f{nullptr, h->row_group, nullptr, nullptr, nullptr, 6 * H, h->x, H, h->xb, H};
+    ctr->slot = LLB_PROF_GEMM_PROJ;
+    if (fused_ln) {
+      f.bias = h->w<float>(L.proj_b[l]), f.shift = mod, f.scale = mod + H, f.gate = mod + 2 * H;
+      LLB_TRY(launch_gemm_ln(h->attn, H, h->w<void>(L.proj_w[l]), H, M, H, H, f, s, ctr));
+    } else {
+      LLB_TRY(gemm_bias_act(h->attn, H, h->w<void>(L.proj_w[l]), H, h->w<float>(L.proj_b[l]), h->y, H, M, H, H, LLB_ACT_NONE, false, s, ctr));
+      a.shift = mod, a.scale = mod + H, a.gate = mod + 2 * H;
+      LLB_TRY(launch_row_ln(a, s));
+      h->launches++;
+    }
     ctr->slot = LLB_PROF_GEMM_FC1;
     LLB_TRY(gemm_bias_act(h->xb, H, h->w<void>(L.fc1_w[l]), H, h->w<float>(L.fc1_b[l]), h->hbuf, F, M, F, H, LLB_ACT_GELU, false, s, ctr));
     ctr->slot = LLB_PROF_GEMM_FC2;
-    LLB_TRY(gemm_bias_act(h->hbuf, F, h->w<void>(L.fc2_w[l]), F, h->w<float>(L.fc2_b[l]), h->y, H, M, H, F, LLB_ACT_NONE, false, s, ctr));
-    a.shift = mod + 3 * H, a.scale = mod + 4 * H, a.gate = mod + 5 * H;
-    LLB_TRY(launch_row_ln(a, s));
-    h->launches++;
+    if (fused_ln && fused_fc2) {
+      f.bias = h->w<float>(L.fc2_b[l]), f.shift = mod + 3 * H, f.scale = mod + 4 * H, f.gate = mod + 5 * H;
+      LLB_TRY(launch_gemm_ln(h->hbuf, F, h->w<void>(L.fc2_w[l]), F, M, H, F, f, s, ctr));
+    } else {
+      LLB_TRY(gemm_bias_act(h->hbuf, F, h->w<void>(L.fc2_w[l]), F, h->w<float>(L.fc2_b[l]), h->y, H, M, H, F, LLB_ACT_NONE, false, s, ctr));
+      a.shift = mod + 3 * H, a.scale = mod + 4 * H, a.gate = mod + 5 * H;
+      LLB_TRY(launch_row_ln(a, s));
+      h->launches++;
+    }
   }
   // 4. output MLP (the LayerNorm / modulation / symmetrisation tail lives in the step kernel)
   ctr->slot = LLB_PROF_GEMM_OTHER;

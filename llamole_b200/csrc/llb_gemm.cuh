@@ -490,7 +490,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 // Host side
 // ------------------------------------------------------------------------------------------------
 // 2-D tensor map: inner dim = cols (contiguous), outer dim = rows; box = box_cols x box_rows;
-// swizzle_bytes in {64, 128} must equal box_cols * elem_bytes.
+// swizzle_bytes in {64, 128} must equal box_cols * elem_bytes; 0 = no swizzle (prefetch-only maps).
 int make_tensor_map_2d(CUtensorMap* out, const void* ptr, int elem_bytes, int rows, int cols, int ld_elems, int box_cols,
                        int box_rows, int swizzle_bytes);
 

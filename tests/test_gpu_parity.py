@@ -50,6 +50,49 @@ def test_gemm_matches_torch(M, N, K, act, out_f32):
     assert mx < tol * max(1.0, float(ref.abs().max())), (mx, rms)
 
 
+# ------------------------------------------------------------------------------------------------ fused GEMM + LN tail
+@pytest.mark.parametrize("M,N,K,group_len", [(1, 256, 64, 50), (300, 1024, 1024, 50), (1000, 1024, 4096, 50), (777, 512, 256, 7),
+                                             (4097, 1024, 1024, 50), (260, 768, 768, 3), (128 * 41 + 5, 1024, 512, 50)])
+def test_gemm_ln_residual_matches_torch(M, N, K, group_len):
+    """x += gate * (LN(A W^T + b) (1 + scale) + shift) against fp32 torch; rows map to modulation rows in runs of
+    `group_len` (3 and 7 force the more-than-4-groups-per-tile path), the last run is a shared 'unconditional' row."""
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    A = (torch.randn(M, K, generator=g) * 0.5).to(DEV).bfloat16()
+    W = (torch.randn(N, K, generator=g) * (1.0 / math.sqrt(K))).to(DEV).bfloat16()
+    bias = (torch.randn(N, generator=g) + 2.0).to(DEV)          # a mean offset stresses the one-pass variance
+    half = (M + 1) // 2
+    groups = torch.arange(M) // group_len
+    n_groups = int(groups[half - 1]) + 2
+    groups = torch.where(torch.arange(M) < half, groups, torch.full_like(groups, n_groups - 1)).to(torch.int32).to(DEV)
+    mod = (torch.randn(n_groups, 3 * N + 8, generator=g) * 0.5).to(DEV)   # an odd leading dimension (multiple of 4)
+    shift, scale, gate = mod[:, :N], mod[:, N:2 * N], mod[:, 2 * N:3 * N]
+    x0 = torch.randn(M, N, generator=g).to(DEV)
+    x = x0.clone()
+    xb = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16)
+    lib = _cabi.lib()
+    _cabi.check(lib.llb_gemm_ln_residual(_cabi.ptr(A), K, _cabi.ptr(W), K, _cabi.ptr(bias), _cabi.ptr(groups), _cabi.ptr(shift),
+                                         _cabi.ptr(scale), _cabi.ptr(gate), mod.shape[1], _cabi.ptr(x), N, _cabi.ptr(xb), N, M, N, K,
+                                         _cabi.stream_ptr()), "llb_gemm_ln_residual")
+    torch.cuda.synchronize()
+    y = (A.double() @ W.double().t() + bias.double())
+    ln = torch.nn.functional.layer_norm(y, (N,), eps=1e-5)
+    gi = groups.long()
+    ref = x0.double() + gate[gi].double() * (ln * (1 + scale[gi].double()) + shift[gi].double())
+    mx, rms = _stats(x, ref)
+    assert not torch.isnan(x).any() and not torch.isnan(xb.float()).any()
+    assert mx < 2e-3 and rms < 2e-4, (mx, rms)      # fp32 accumulation order + one-pass variance
+    assert torch.equal(xb, x.bfloat16())
+
+
+def test_gemm_ln_residual_rejects_unsupported_width():
+    z = torch.zeros(8, 320, device=DEV)
+    lib = _cabi.lib()
+    st = lib.llb_gemm_ln_residual(_cabi.ptr(z.bfloat16()), 320, _cabi.ptr(z.bfloat16()), 320, None, _cabi.ptr(z.int()), _cabi.ptr(z),
+                                  _cabi.ptr(z), _cabi.ptr(z), 320, _cabi.ptr(z), 320, _cabi.ptr(z.bfloat16()), 320, 8, 320, 320,
+                                  _cabi.stream_ptr())
+    assert st != 0 and b"gemm_ln" in lib.llb_last_error()
+
+
 # ------------------------------------------------------------------------------------------------ GraphDiT
 @pytest.fixture(scope="module")
 def dit(dit_small):
