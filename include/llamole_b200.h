@@ -76,6 +76,15 @@ int llb_gemm_bf16(const void* A, int lda, const void* W, int ldw, const float* b
 int llb_gemm_ln_residual(const void* A, int lda, const void* W, int ldw, const float* bias, const int32_t* row_group,
                          const float* shift, const float* scale, const float* gate, int mod_ld, float* x, int ldx,
                          void* xb, int ldxb, int M, int N, int K, llb_stream_t stream);
+/* Same operation for N = 1024 on CTA pairs (tcgen05.mma.cta_group::2): four pairs share a 256-row block and exchange
+ * the LayerNorm statistics through `workspace` (llb_gemm_ln_workspace_bytes bytes, 128-byte aligned, owned by the caller,
+ * not shared with a concurrent launch).  The faster of the two for K >= 1024; the GraphDiT sampler uses it for both
+ * block halves. */
+int llb_gemm_ln_workspace_bytes(size_t* bytes);
+int llb_gemm_ln_residual_ws(const void* A, int lda, const void* W, int ldw, const float* bias, const int32_t* row_group,
+                            const float* shift, const float* scale, const float* gate, int mod_ld, float* x, int ldx,
+                            void* xb, int ldxb, int M, int N, int K, void* workspace, size_t workspace_bytes,
+                            llb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * GraphDiT sampler  (graph_decoder/diffusion_model.py:252-399, transformer.py:93-187, layers.py:56-116,

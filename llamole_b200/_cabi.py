@@ -69,6 +69,8 @@ SIGNATURES = {
     "llb_profile_slot_name": (C.c_char_p, [_I]),
     "llb_gemm_bf16": (_I, [_P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "llb_gemm_ln_residual": (_I, [_P, _I, _P, _I, _P, _P, _P, _P, _P, _I, _P, _I, _P, _I, _I, _I, _I, _P]),
+    "llb_gemm_ln_workspace_bytes": (_I, [C.POINTER(_SZ)]),
+    "llb_gemm_ln_residual_ws": (_I, [_P, _I, _P, _I, _P, _P, _P, _P, _P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _SZ, _P]),
     "llb_dit_packed_bytes": (_I, [C.POINTER(DitConfig), C.POINTER(_SZ)]),
     "llb_dit_pack_weights": (_I, [C.POINTER(DitConfig), C.POINTER(DitWeights), _P, _SZ, _P]),
     "llb_dit_create": (_I, [C.POINTER(DitConfig), _P, _SZ, C.POINTER(_P)]),

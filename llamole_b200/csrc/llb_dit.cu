@@ -211,6 +211,7 @@ struct llb_dit {
   int32_t* mol_off = nullptr;    // (B+1)
   int32_t* row_mol = nullptr;    // (Mtok)
   int32_t* row_group = nullptr;  // (M): modulation row of each token row
+  void* ln_sync = nullptr;       // statistics-exchange workspace of the CTA-pair GEMM + LayerNorm kernel
   template <class T>
   const T* w(size_t off) const { return reinterpret_cast<const T*>(blob + off); }
 };
@@ -247,6 +248,7 @@ static int dit_carve(llb_dit* h, void* ws, size_t ws_bytes, int B, int Mtok, siz
   h->mol_off = a.take<int32_t>(B + 1);
   h->row_mol = a.take<int32_t>(Mtok > 0 ? Mtok : 1);
   h->row_group = a.take<int32_t>(M > 0 ? M : 1);
+  h->ln_sync = a.take<uint8_t>(gemm_ln_pair_workspace_bytes());
   *need = align_up(a.off, 256);
   return LLB_OK;
 }
@@ -297,9 +299,13 @@ static int dit_forward(llb_dit* h, int t, cudaStream_t s) {
   // 3. transformer blocks
   const float q_scale = 1.4426950408889634f / sqrtf((float)DIT_DH);
   const bool fused_ln = gemm_ln_supported(H, H) && gemm_ln_supported(H, F) && gemm_ln_enabled();
-  // With K = 4 H the GEMM main loop dominates and the CTA-pair kernel's is faster than the cluster kernel's, which more
-  // than pays for the separate row kernel; LLB_FUSED_LN=2 fuses fc2 as well (A/B comparison).
-  const bool fused_fc2 = gemm_ln_mode() == 2;
+  // LLB_FUSED_LN: 0 = GEMM + row kernel; 1 = fused, 4-CTA cluster kernel (projection only: with K = 4 H its single-CTA
+  // main loop loses more than the row kernel costs); 2 = cluster kernel for both halves; 3 (default) = fused on the
+  // CTA-pair main loop for both halves when H = 1024, else as 1.
+  const int ln_mode = gemm_ln_mode();
+  const bool fused_pair = fused_ln && (ln_mode == 3 || ln_mode == 4) && H == 4 * GLN_BN;   // 4 = pair kernel, projection only
+  const bool fused_fc2 = ln_mode == 2 || (fused_pair && ln_mode == 3);
+  const size_t ln_sync_bytes = gemm_ln_pair_workspace_bytes();
   for (int l = 0; l < D; ++l) {
     const float* mod = h->mod + (size_t)l * (B + 1) * 6 * H;
     ctr->slot = LLB_PROF_GEMM_QKV;
@@ -320,7 +326,8 @@ static int dit_forward(llb_dit* h, int t, cudaStream_t s) {
     ctr->slot = LLB_PROF_GEMM_PROJ;
     if (fused_ln) {
       f.bias = h->w<float>(L.proj_b[l]), f.shift = mod, f.scale = mod + H, f.gate = mod + 2 * H;
-      LLB_TRY(launch_gemm_ln(h->attn, H, h->w<void>(L.proj_w[l]), H, M, H, H, f, s, ctr));
+      if (fused_pair) LLB_TRY(launch_gemm_ln_pair(h->attn, H, h->w<void>(L.proj_w[l]), H, M, H, H, f, h->ln_sync, ln_sync_bytes, s, ctr));
+      else LLB_TRY(launch_gemm_ln(h->attn, H, h->w<void>(L.proj_w[l]), H, M, H, H, f, s, ctr));
     } else {
       LLB_TRY(gemm_bias_act(h->attn, H, h->w<void>(L.proj_w[l]), H, h->w<float>(L.proj_b[l]), h->y, H, M, H, H, LLB_ACT_NONE, false, s, ctr));
       a.shift = mod, a.scale = mod + H, a.gate = mod + 2 * H;
@@ -332,7 +339,8 @@ static int dit_forward(llb_dit* h, int t, cudaStream_t s) {
     ctr->slot = LLB_PROF_GEMM_FC2;
     if (fused_ln && fused_fc2) {
       f.bias = h->w<float>(L.fc2_b[l]), f.shift = mod + 3 * H, f.scale = mod + 4 * H, f.gate = mod + 5 * H;
-      LLB_TRY(launch_gemm_ln(h->hbuf, F, h->w<void>(L.fc2_w[l]), F, M, H, F, f, s, ctr));
+      if (fused_pair) LLB_TRY(launch_gemm_ln_pair(h->hbuf, F, h->w<void>(L.fc2_w[l]), F, M, H, F, f, h->ln_sync, ln_sync_bytes, s, ctr));
+      else LLB_TRY(launch_gemm_ln(h->hbuf, F, h->w<void>(L.fc2_w[l]), F, M, H, F, f, s, ctr));
     } else {
       LLB_TRY(gemm_bias_act(h->hbuf, F, h->w<void>(L.fc2_w[l]), F, h->w<float>(L.fc2_b[l]), h->y, H, M, H, F, LLB_ACT_NONE, false, s, ctr));
       a.shift = mod + 3 * H, a.scale = mod + 4 * H, a.gate = mod + 5 * H;

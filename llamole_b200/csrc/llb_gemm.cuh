@@ -317,10 +317,12 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
                ::"r"(smem_u32(bar)), "h"((uint16_t)3)
                : "memory");
 }
+// Arrive on an mbarrier of CTA `cta` of the cluster.  Relaxed: the accumulator hand-over it signals is ordered by
+// tcgen05.wait::ld + tcgen05.fence::before_thread_sync, and a release at cluster scope costs a MEMBAR.GPU per arrive.
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 
 template <bool TMA_STORE, class Epi>

@@ -9,7 +9,7 @@ namespace {
 
 #ifdef LLB_GEMM_TRACE
 __device__ long long* g_gln_trace = nullptr;   // [tile][16] stamps of CTA 0 (tools/gemm_ln_trace.cu)
-__device__ int g_gln_exp = 0;                  // knock-outs: 1 no x store, 2 no xb store, 4 no residual reload
+__device__ int g_gln_exp = 0;                  // knock-outs: 1 no x store, 2 no xb store, 4 no residual reload, 8 no pass 2, 16 empty epilogue (pair kernel)
 #define GLN_TRACE(tile_idx, slot, value) \
   do { if (g_gln_trace && blockIdx.x == 0 && (tile_idx) < 64) g_gln_trace[(size_t)(tile_idx) * 16 + (slot)] = (value); } while (0)
 #define GLN_EXP(bit) ((g_gln_exp & (bit)) != 0)
@@ -159,14 +159,14 @@ __device__ __forceinline__ void gln_pass2(const GlnPass2& a, const CUtensorMap* 
       sts128(xa, o);
       sts64(a.xbstg + rr * 64 + ((((sl >> 1) ^ (rr >> 1)) & 3) << 4) + (sl & 1) * 8, pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
       // next chunk's residual segment: in flight during that chunk's TMEM load and arithmetic
-      if (c + 32 < GLN_BN / 2 && it * 4 < a.rows_left) res[it] = *reinterpret_cast<const float4*>(xp + 32);
+      if (c + 32 < GLN_BN / 2 && it * 4 < a.rows_left && !GLN_EXP(4)) res[it] = *reinterpret_cast<const float4*>(xp + 32);
       xp += a.xstride;
     }
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
-      tma_store_2d(tmX, reinterpret_cast<const void*>(__cvta_shared_to_generic(a.xstg)), a.gcol + c, a.grow);
-      tma_store_2d(tmXb, reinterpret_cast<const void*>(__cvta_shared_to_generic(a.xbstg)), a.gcol + c, a.grow);
+      if (!GLN_EXP(1)) tma_store_2d(tmX, reinterpret_cast<const void*>(__cvta_shared_to_generic(a.xstg)), a.gcol + c, a.grow);
+      if (!GLN_EXP(2)) tma_store_2d(tmXb, reinterpret_cast<const void*>(__cvta_shared_to_generic(a.xbstg)), a.gcol + c, a.grow);
       bulk_commit();
     }
 #ifdef LLB_GEMM_TRACE
@@ -182,6 +182,84 @@ __device__ __forceinline__ void gln_pass2(const GlnPass2& a, const CUtensorMap* 
     GLN_TRACE(a.trace_tile, 14, tt3);
   }
 #endif
+}
+
+// Modulation stager, one warp, one tile: which modulation rows do the tile's 128 token rows use (runs of equal
+// row_group), stage gate*(1+scale) and gate*shift of those rows (this CTA's 256 columns) in shared memory, and pull the
+// CTA's block of the residual stream into L2 for the epilogue's pass 2.
+__device__ __forceinline__ void gln_stage_tile(const GemmLnArgs& e, const CUtensorMap* tmXpf, float* mod_dst, int2* rowinfo, int* glist,
+                                               int m0, int n0, int M, int lane) {
+  constexpr int BN = GLN_BN;
+  int cnt = 0;
+#pragma unroll
+  for (int seg = 0; seg < 4; ++seg) {
+    const int r = m0 + seg * 32 + lane;
+    const int rc = r < M ? r : M - 1;
+    const int g = __ldg(e.row_group + rc);
+    const int gp = (rc > m0) ? __ldg(e.row_group + rc - 1) : g;
+    const int flag = (r < M && g != gp) ? 1 : 0;
+    const uint32_t mask = __ballot_sync(0xffffffffu, flag);
+    const int gi = cnt + __popc(mask & (0xffffffffu >> (31 - lane)));
+    cnt += __popc(mask);
+    rowinfo[seg * 32 + lane] = make_int2(gi, g);
+    if ((flag || (seg == 0 && lane == 0)) && gi < GLN_MAX_GROUPS) glist[gi] = g;
+  }
+  const int ngroups = cnt + 1;
+  if (lane == 0) {
+    glist[4] = ngroups;
+    if (m0 < M) l2_prefetch_tile(tmXpf, n0, m0);   // this CTA's 128 x 256 block of the residual stream
+  }
+  __syncwarp();
+  if (ngroups <= GLN_MAX_GROUPS) {
+    // mod_dst[k][0][col] = gate * (1 + scale), [k][1][col] = gate * shift; each lane owns 8 columns per group
+    float4 sh[GLN_MAX_GROUPS][2], sc[GLN_MAX_GROUPS][2], gt[GLN_MAX_GROUPS][2];
+#pragma unroll
+    for (int k = 0; k < GLN_MAX_GROUPS; ++k) {
+      if (k < ngroups) {
+        const size_t off = (size_t)glist[k] * e.mod_ld + n0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int col = h * 128 + lane * 4;
+          sh[k][h] = __ldg(reinterpret_cast<const float4*>(e.shift + off + col));
+          sc[k][h] = __ldg(reinterpret_cast<const float4*>(e.scale + off + col));
+          gt[k][h] = __ldg(reinterpret_cast<const float4*>(e.gate + off + col));
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < GLN_MAX_GROUPS; ++k) {
+      if (k < ngroups) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int col = h * 128 + lane * 4;
+          const float4 g4 = gt[k][h], s4 = sc[k][h], h4 = sh[k][h];
+          *reinterpret_cast<float4*>(mod_dst + (k * 2 + 0) * BN + col) =
+              make_float4((1.0f + s4.x) * g4.x, (1.0f + s4.y) * g4.y, (1.0f + s4.z) * g4.z, (1.0f + s4.w) * g4.w);
+          *reinterpret_cast<float4*>(mod_dst + (k * 2 + 1) * BN + col) = make_float4(h4.x * g4.x, h4.y * g4.y, h4.z * g4.z, h4.w * g4.w);
+        }
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// Pass 1 of the epilogue: sum and sum of squares of (accumulator + bias) over this warp's 128 columns of its row.
+__device__ __forceinline__ float2 gln_pass1(uint32_t t_row, uint32_t bias_s) {
+  float v[32];
+  float s = 0.f, ss = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < GLN_BN / 2; c += 32) {
+    tmem_ld32(t_row + c, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float4 b = lds128(bias_s + (c + i) * 4);
+      const float a0 = v[i] + b.x, a1 = v[i + 1] + b.y, a2 = v[i + 2] + b.z, a3 = v[i + 3] + b.w;
+      s += (a0 + a1) + (a2 + a3);
+      ss = fmaf(a0, a0, ss), ss = fmaf(a1, a1, ss), ss = fmaf(a2, a2, ss), ss = fmaf(a3, a3, ss);
+    }
+  }
+  return make_float2(s, ss);
 }
 
 // Warp roles: 0..7 epilogue, 8 TMA producer, 9 MMA issuer, 10 TMEM allocator, 11 modulation stager.
@@ -316,58 +394,7 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     for (int mt = cluster_id; mt < num_m; mt += num_clusters) {
       const int m0 = mt * GEMM_BM;
       mbar_wait(&mod_empty[st], ph ^ 1);
-      int cnt = 0;
-#pragma unroll
-      for (int seg = 0; seg < 4; ++seg) {
-        const int r = m0 + seg * 32 + lane;
-        const int rc = r < M ? r : M - 1;
-        const int g = __ldg(e.row_group + rc);
-        const int gp = (rc > m0) ? __ldg(e.row_group + rc - 1) : g;
-        const int flag = (r < M && g != gp) ? 1 : 0;
-        const uint32_t mask = __ballot_sync(0xffffffffu, flag);
-        const int gi = cnt + __popc(mask & (0xffffffffu >> (31 - lane)));
-        cnt += __popc(mask);
-        rowinfoS[st * GEMM_BM + seg * 32 + lane] = make_int2(gi, g);
-        if ((flag || (seg == 0 && lane == 0)) && gi < GLN_MAX_GROUPS) glistS[st * 8 + gi] = g;
-      }
-      const int ngroups = cnt + 1;
-      if (lane == 0) {
-        glistS[st * 8 + 4] = ngroups;
-        l2_prefetch_tile(&tmXpf, n0, m0);   // this CTA's 128 x 256 block of the residual stream
-      }
-      __syncwarp();
-      if (ngroups <= GLN_MAX_GROUPS) {
-        // modS[st][k][0][col] = gate * (1 + scale), [k][1][col] = gate * shift; each lane owns 8 columns per group
-        float* dst = modS + (size_t)st * S::MOD_STAGE_FLOATS;
-        float4 sh[GLN_MAX_GROUPS][2], sc[GLN_MAX_GROUPS][2], gt[GLN_MAX_GROUPS][2];
-#pragma unroll
-        for (int k = 0; k < GLN_MAX_GROUPS; ++k) {
-          if (k < ngroups) {
-            const size_t off = (size_t)glistS[st * 8 + k] * e.mod_ld + n0;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int col = h * 128 + lane * 4;
-              sh[k][h] = __ldg(reinterpret_cast<const float4*>(e.shift + off + col));
-              sc[k][h] = __ldg(reinterpret_cast<const float4*>(e.scale + off + col));
-              gt[k][h] = __ldg(reinterpret_cast<const float4*>(e.gate + off + col));
-            }
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < GLN_MAX_GROUPS; ++k) {
-          if (k < ngroups) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int col = h * 128 + lane * 4;
-              const float4 g4 = gt[k][h], s4 = sc[k][h], h4 = sh[k][h];
-              *reinterpret_cast<float4*>(dst + (k * 2 + 0) * BN + col) =
-                  make_float4((1.0f + s4.x) * g4.x, (1.0f + s4.y) * g4.y, (1.0f + s4.z) * g4.z, (1.0f + s4.w) * g4.w);
-              *reinterpret_cast<float4*>(dst + (k * 2 + 1) * BN + col) = make_float4(h4.x * g4.x, h4.y * g4.y, h4.z * g4.z, h4.w * g4.w);
-            }
-          }
-        }
-      }
-      __syncwarp();
+      gln_stage_tile(e, &tmXpf, modS + (size_t)st * S::MOD_STAGE_FLOATS, rowinfoS + st * GEMM_BM, glistS + st * 8, m0, n0, M, lane);
       if (lane == 0) mbar_arrive(&mod_full[st]);
       if (++st == 2) {
         st = 0;
@@ -406,23 +433,7 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       if (tr) GLN_TRACE(tcount, 2, clock64());
       tc_fence_after();
       a.t_row = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16) + cbase;
-      {
-        float v[32];
-        float s = 0.f, ss = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < BN / 2; c += 32) {
-          tmem_ld32(a.t_row + c, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 b = lds128(a.bias_s + (c + i) * 4);
-            const float a0 = v[i] + b.x, a1 = v[i + 1] + b.y, a2 = v[i + 2] + b.z, a3 = v[i + 3] + b.w;
-            s += (a0 + a1) + (a2 + a3);
-            ss = fmaf(a0, a0, ss), ss = fmaf(a1, a1, ss), ss = fmaf(a2, a2, ss), ss = fmaf(a3, a3, ss);
-          }
-        }
-        partS[ch * GEMM_BM + rloc] = make_float2(s, ss);
-      }
+      partS[ch * GEMM_BM + rloc] = gln_pass1(a.t_row, a.bias_s);
       epi_bar_sync();
       if (ch == 0) {
         // combine the two column halves; each of warps 0..3 ships its 32 rows (256 bytes) to every CTA of the cluster
@@ -495,13 +506,314 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// N = 1024 variant on the CTA-pair (cta_group::2) main loop.
+//
+// The cluster kernel above cannot use tcgen05.mma.cta_group::2: a pair splits the M dimension, so one pair owns a
+// 256-row x 256-column block, a full 1024-column row then spans four pairs = a cluster of 8, and only 15 such clusters
+// fit the B200 (120 of 148 SMs).  Here FOUR INDEPENDENT PAIRS (four 2-CTA clusters, 72 of 74 pairs in use) form a
+// group that owns one 256-row block; CTA (slice s, rank r) holds rows [128 r, +128) x columns [256 s, +256).  The row
+// statistics are exchanged between the four CTAs of equal rank through global memory (L2): every statistics warp
+// writes its 32 rows, releases a per-(group, rank) counter (fence + atomic add) and every epilogue warp polls the
+// counter with acquire loads.  The ~2.5k cycles of round trips sit inside the epilogue, which the second TMEM
+// accumulator stage overlaps with the next tile's MMAs.  All CTAs of the persistent grid must be co-resident (the grid
+// is launched cooperatively, never larger than the device holds).
+// ------------------------------------------------------------------------------------------------------------------
+struct GlnPairSmem {
+  static constexpr int STAGES = 4;
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;            // 16 KB: this CTA's 128 rows
+  static constexpr int B_BYTES = (GLN_BN / 2) * GEMM_BK * 2;       // 16 KB: this CTA's half of the pair's 256 W rows
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int XSTG_PER_WARP = 32 * 32 * 4;
+  static constexpr int XBSTG_PER_WARP = 32 * 32 * 2;
+  static constexpr int MOD_STAGE_FLOATS = GLN_MAX_GROUPS * 2 * GLN_BN;
+  static constexpr int OFF_XSTG = STAGES * STAGE_BYTES;
+  static constexpr int OFF_XBSTG = OFF_XSTG + GEMM_EPI_WARPS * XSTG_PER_WARP;
+  static constexpr int OFF_MOD = OFF_XBSTG + GEMM_EPI_WARPS * XBSTG_PER_WARP;
+  static constexpr int OFF_BIAS = OFF_MOD + 2 * MOD_STAGE_FLOATS * 4;
+  static constexpr int OFF_PART = OFF_BIAS + GLN_BN * 4;
+  static constexpr int OFF_ROWINFO = OFF_PART + 2 * GEMM_BM * 8;
+  static constexpr int OFF_GLIST = OFF_ROWINFO + 2 * GEMM_BM * 8;
+  static constexpr int OFF_BARS = OFF_GLIST + 64;
+  static constexpr int TOTAL = OFF_BARS + 256 + 1024;
+};
+static_assert(GlnPairSmem::TOTAL <= 232448, "gemm_ln pair kernel shared memory exceeds the 227 KB per-CTA limit");
+
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
+                    const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXb,
+                    const __grid_constant__ CUtensorMap tmXpf, int M, int K, int G, GemmLnArgs e, uint32_t* sync_cnt,
+                    float2* sync_stats) {
+  using S = GlnPairSmem;
+  constexpr int STAGES = S::STAGES;
+  constexpr int BN = GLN_BN;
+  constexpr int NS = 4;   // column slices of 256 = pairs per group
+  const uint32_t rank = cluster_rank();
+  const int pair = blockIdx.x >> 1;
+  const int grp = pair / NS, slice = pair % NS;
+  if (grp >= G) return;   // spare pair(s): both CTAs leave together, nothing was set up yet
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* smA = smem;
+  uint8_t* smB = smem + STAGES * S::A_BYTES;
+  float* modS = reinterpret_cast<float*>(smem + S::OFF_MOD);
+  float* biasS = reinterpret_cast<float*>(smem + S::OFF_BIAS);
+  float2* partS = reinterpret_cast<float2*>(smem + S::OFF_PART);
+  int2* rowinfoS = reinterpret_cast<int2*>(smem + S::OFF_ROWINFO);
+  int* glistS = reinterpret_cast<int*>(smem + S::OFF_GLIST);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BARS);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tmem_full = bars + 2 * STAGES;
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2;
+  uint64_t* mod_full = bars + 2 * STAGES + 4;
+  uint64_t* mod_empty = bars + 2 * STAGES + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_mb = (M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+  const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
+  const int n0 = slice * BN;
+
+  if (warp == GEMM_EPI_WARPS && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmBh);
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmXb);
+    tma_prefetch_desc(&tmXpf);
+    for (int st = 0; st < STAGES; ++st) {
+      mbar_init(&full[st], 1);
+      mbar_init(&empty[st], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 2 * GEMM_EPI_WARPS);
+      mbar_init(&mod_full[a], 1);
+      mbar_init(&mod_empty[a], GEMM_EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (threadIdx.x < BN) biasS[threadIdx.x] = e.bias ? e.bias[n0 + threadIdx.x] : 0.0f;
+  cluster_sync_all();
+  if (warp == GEMM_EPI_WARPS + 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(2 * BN))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == GEMM_EPI_WARPS) {
+    // ---------------- TMA producer (both CTAs; completion bytes go to the leader's full[]) ----------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int nB = n0 + (int)rank * (BN / 2);
+      for (int mb = grp; mb < num_mb; mb += G) {
+        const int m0 = mb * 2 * GEMM_BM + (int)rank * GEMM_BM;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * S::STAGE_BYTES);
+          tma_load_2d_2sm(smA + stage * S::A_BYTES, &tmA, &full[stage], kb * GEMM_BK, m0);
+          tma_load_2d_2sm(smB + stage * S::B_BYTES, &tmBh, &full[stage], kb * GEMM_BK, nB);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == GEMM_EPI_WARPS + 1) {
+    // ---------------- MMA issuer (leader CTA only) ----------------
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * GEMM_BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      int tcount = 0;
+      for (int mb = grp; mb < num_mb; mb += G, ++tcount) {
+        GLN_TRACE(tcount, 8, clock64());
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        GLN_TRACE(tcount, 9, clock64());
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smA + stage * S::A_BYTES);
+          const uint32_t b_addr = smem_u32(smB + stage * S::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k)
+            umma_bf16_2sm(d_tmem, umma_desc_k128(a_addr + k * 32), umma_desc_k128(b_addr + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_2sm(&empty[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_2sm(&tmem_full[acc]);
+        GLN_TRACE(tcount, 10, clock64());
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == GEMM_EPI_WARPS + 3) {
+    // ---------------- modulation stager ----------------
+    int st = 0;
+    uint32_t ph = 0;
+    for (int mb = grp; mb < num_mb; mb += G) {
+      const int m0 = mb * 2 * GEMM_BM + (int)rank * GEMM_BM;
+      mbar_wait(&mod_empty[st], ph ^ 1);
+      gln_stage_tile(e, &tmXpf, modS + (size_t)st * S::MOD_STAGE_FLOATS, rowinfoS + st * GEMM_BM, glistS + st * 8, m0, n0, M, lane);
+      if (lane == 0) mbar_arrive(&mod_full[st]);
+      if (++st == 2) {
+        st = 0;
+        ph ^= 1;
+      }
+    }
+  } else if (warp < GEMM_EPI_WARPS) {
+    // ---------------- epilogue ----------------
+    const int q = warp & 3, ch = warp >> 2;
+    const int rloc = q * 32 + lane;
+    const int cbase = ch * (BN / 2);
+    const float inv_n = 1.0f / (float)(NS * BN);
+    const int sl = lane & 7, rsub = lane >> 3;
+    GlnPass2 a;
+    a.xstg = smem_u32(smem + S::OFF_XSTG + warp * S::XSTG_PER_WARP);
+    a.xbstg = smem_u32(smem + S::OFF_XBSTG + warp * S::XBSTG_PER_WARP);
+    a.bias_s = smem_u32(biasS + cbase);
+    a.xstride = (size_t)4 * e.ldx;
+    a.gcol = n0 + cbase;
+    uint32_t* my_cnt = sync_cnt + (size_t)(grp * 2 + rank) * 32;   // one 128-byte line per (group, rank)
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int tcount = 0;
+    const bool tr = warp == 0 && lane == 0;
+    for (int mb = grp; mb < num_mb; mb += G, ++tcount) {
+      const int m0 = mb * 2 * GEMM_BM + (int)rank * GEMM_BM;
+      if (tr) GLN_TRACE(tcount, 0, clock64());
+      mbar_wait(&mod_full[acc], acc_phase);
+      const int2 info = rowinfoS[acc * GEMM_BM + rloc];
+      const bool staged = glistS[acc * 8 + 4] <= GLN_MAX_GROUPS;
+      if (tr) GLN_TRACE(tcount, 1, clock64());
+      mbar_wait(&tmem_full[acc], acc_phase);
+      if (tr) GLN_TRACE(tcount, 2, clock64());
+      tc_fence_after();
+      a.t_row = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16) + cbase;
+      if (GLN_EXP(16)) {   // knock-out: empty epilogue (main loop alone)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive_cluster(&tmem_empty[acc], 0);
+          mbar_arrive(&mod_empty[acc]);
+        }
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+        continue;
+      }
+      partS[ch * GEMM_BM + rloc] = gln_pass1(a.t_row, a.bias_s);
+      epi_bar_sync();
+      // statistics slots: [group][tile parity][rank][slice][128 rows]
+      float2* gstats = sync_stats + (size_t)((grp * 2 + (tcount & 1)) * 2 + rank) * NS * GEMM_BM;
+      if (ch == 0) {
+        const float2 p0 = partS[rloc], p1 = partS[GEMM_BM + rloc];
+        gstats[slice * GEMM_BM + rloc] = make_float2(p0.x + p1.x, p0.y + p1.y);
+        __syncwarp();
+        if (lane == 0) {
+          __threadfence();
+          atomicAdd(my_cnt, 1u);
+        }
+      }
+      if (tr) GLN_TRACE(tcount, 3, clock64());
+      // first residual chunk: in flight while the statistics travel
+      const int row0 = m0 + q * 32 + rsub;
+      a.rows_left = M - row0;
+      a.grow = m0 + q * 32;
+      a.xrow = e.x + (size_t)row0 * e.ldx + n0 + cbase + sl * 4;
+      float4 res[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it)
+        res[it] = (it * 4 < a.rows_left) ? *reinterpret_cast<const float4*>(a.xrow + it * a.xstride) : make_float4(0.f, 0.f, 0.f, 0.f);
+      // all four slices of this rank have published tile `tcount`: 4 CTAs x 4 statistics warps each
+      if (lane == 0) {
+        const uint32_t target = 16u * (uint32_t)(tcount + 1);
+        long long start = clock64();
+        while ((int)(ld_acquire_gpu(my_cnt) - target) < 0) {
+          if (clock64() - start > 8000000000ll) {
+            printf("llamole_b200: statistics exchange timed out (block %d warp %d)\n", blockIdx.x, warp);
+            __trap();
+          }
+        }
+      }
+      __syncwarp();
+      if (tr) GLN_TRACE(tcount, 4, clock64());
+      {
+        float s = 0.f, ss = 0.f;
+#pragma unroll
+        for (int src = 0; src < NS; ++src) {
+          const float2 p = __ldcg(gstats + src * GEMM_BM + rloc);
+          s += p.x, ss += p.y;
+        }
+        const float mean = s * inv_n;
+        const float var = fmaxf(ss * inv_n - mean * mean, 0.0f);
+        a.rstd = rsqrtf(var + 1e-5f);
+        a.nmr = -mean * a.rstd;
+      }
+      a.trace_tile = tr ? tcount : -1;
+      if (GLN_EXP(8)) {
+      } else if (staged) {
+        a.mod_s = smem_u32(modS + (size_t)acc * S::MOD_STAGE_FLOATS + (size_t)info.x * 2 * BN + cbase);
+        gln_pass2<true>(a, &tmX, &tmXb, res, lane);
+      } else {
+        const size_t off = (size_t)info.y * e.mod_ld + n0 + cbase;
+        a.g_shift = e.shift + off, a.g_scale = e.scale + off, a.g_gate = e.gate + off;
+        gln_pass2<false>(a, &tmX, &tmXb, res, lane);
+      }
+      if (tr) GLN_TRACE(tcount, 5, clock64());
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive_cluster(&tmem_empty[acc], 0);
+        mbar_arrive(&mod_empty[acc]);
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+    if (lane == 0) bulk_wait_all();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == GEMM_EPI_WARPS + 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)) : "memory");
+  }
+}
+
 }  // namespace
 
 int gemm_ln_mode() {
   static int mode = -1;
   if (mode < 0) {
     const char* v = getenv("LLB_FUSED_LN");
-    mode = (v && v[0] >= '0' && v[0] <= '2') ? v[0] - '0' : 1;
+    mode = (v && v[0] >= '0' && v[0] <= '4') ? v[0] - '0' : 3;
   }
   return mode;
 }
@@ -559,6 +871,78 @@ int launch_gemm_ln(const void* A, int lda, const void* W, int ldw, int M, int N,
   return LLB_OK;
 }
 
+
+size_t gemm_ln_pair_workspace_bytes() {
+  // counters: one 128-byte line per (group, rank); statistics: [group][2 parities][2 ranks][4 slices][128] float2
+  return (size_t)GLN_PAIR_MAX_GROUPS * 2 * 128 + (size_t)GLN_PAIR_MAX_GROUPS * 2 * 2 * 4 * GEMM_BM * sizeof(float2);
+}
+
+int launch_gemm_ln_pair(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const GemmLnArgs& e, void* sync_ws,
+                        size_t sync_bytes, cudaStream_t stream, GemmCounters* ctr) {
+  if (M <= 0) return LLB_OK;
+  LLB_CHECK_ARG(N == 4 * GLN_BN && K % 8 == 0, "gemm_ln_pair: N=%d must be 1024 and K=%d a multiple of 8", N, K);
+  LLB_CHECK_ARG(lda % 8 == 0 && ldw % 8 == 0 && e.ldx % 4 == 0 && e.ldxb % 8 == 0 && e.mod_ld % 4 == 0,
+                "gemm_ln_pair: leading dimensions must keep rows 16-byte aligned");
+  LLB_CHECK_ARG(e.row_group && e.shift && e.scale && e.gate && e.x && e.xb, "gemm_ln_pair: null operand");
+  LLB_CHECK_ARG(sync_ws && sync_bytes >= gemm_ln_pair_workspace_bytes() && (reinterpret_cast<uintptr_t>(sync_ws) & 127) == 0,
+                "gemm_ln_pair: the exchange workspace needs %zu bytes, 128-byte aligned", gemm_ln_pair_workspace_bytes());
+  LLB_CHECK_ARG(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(e.x) |
+                  reinterpret_cast<uintptr_t>(e.xb) | reinterpret_cast<uintptr_t>(e.shift) | reinterpret_cast<uintptr_t>(e.scale) |
+                  reinterpret_cast<uintptr_t>(e.gate)) & 15) == 0,
+                "gemm_ln_pair: operands must be 16-byte aligned");
+  LLB_CHECK_ARG(A != (const void*)e.xb, "gemm_ln_pair: the A operand must not alias the bf16 output");
+  CUtensorMap tmA, tmBh, tmX, tmXb, tmXpf;
+  LLB_TRY(make_tensor_map_2d(&tmA, A, 2, M, K, lda, GEMM_BK, GEMM_BM, 128));
+  LLB_TRY(make_tensor_map_2d(&tmBh, W, 2, N, K, ldw, GEMM_BK, GLN_BN / 2, 128));
+  LLB_TRY(make_tensor_map_2d(&tmX, e.x, 4, M, N, e.ldx, 32, 32, 128));
+  LLB_TRY(make_tensor_map_2d(&tmXb, e.xb, 2, M, N, e.ldxb, 32, 32, 64));
+  LLB_TRY(make_tensor_map_2d(&tmXpf, e.x, 4, M, N, e.ldx, GLN_BN, GEMM_BM, 0));
+  static bool configured = false;
+  static int max_groups = 0;
+  static bool cooperative = true;
+  if (!configured) {
+    LLB_CUDA_OK(cudaFuncSetAttribute(gemm_ln_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GlnPairSmem::TOTAL));
+    cudaLaunchConfig_t q = {};
+    q.blockDim = dim3(GEMM_THREADS), q.dynamicSmemBytes = GlnPairSmem::TOTAL, q.gridDim = dim3(2 * (num_sms() / 2));
+    int n = 0;
+    LLB_CUDA_OK(cudaOccupancyMaxActiveClusters(&n, gemm_ln_pair_kernel, &q));
+    max_groups = n / 4 < GLN_PAIR_MAX_GROUPS ? n / 4 : GLN_PAIR_MAX_GROUPS;
+    LLB_CHECK_ARG(max_groups > 0, "gemm_ln_pair: fewer than four CTA pairs fit on this device");
+    configured = true;
+  }
+  const int num_mb = ceil_div(M, 2 * GEMM_BM);
+  const int G = num_mb < max_groups ? num_mb : max_groups;
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(sync_ws);
+  float2* stats = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(sync_ws) + (size_t)GLN_PAIR_MAX_GROUPS * 2 * 128);
+  LLB_CUDA_OK(cudaMemsetAsync(cnt, 0, (size_t)GLN_PAIR_MAX_GROUPS * 2 * 128, stream));
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;   // every CTA of the grid is resident: the groups spin on each other
+  attr[0].val.cooperative = 1;
+  cfg.blockDim = dim3(GEMM_THREADS), cfg.dynamicSmemBytes = GlnPairSmem::TOTAL, cfg.stream = stream, cfg.attrs = attr;
+  cfg.gridDim = dim3(2 * 4 * G);
+  {
+    ProfScope prof(ctr ? ctr->slot : LLB_PROF_GEMM_OTHER, stream);
+    cudaError_t err = cudaErrorNotSupported;
+    if (cooperative) {
+      cfg.numAttrs = 1;
+      err = cudaLaunchKernelEx(&cfg, gemm_ln_pair_kernel, tmA, tmBh, tmX, tmXb, tmXpf, M, K, G, e, cnt, stats);
+      if (err != cudaSuccess) {
+        (void)cudaGetLastError();
+        cooperative = false;   // this driver does not combine clusters with cooperative launch; the grid still fits the device
+      }
+    }
+    if (!cooperative) {
+      cfg.numAttrs = 0;
+      err = cudaLaunchKernelEx(&cfg, gemm_ln_pair_kernel, tmA, tmBh, tmX, tmXb, tmXpf, M, K, G, e, cnt, stats);
+    }
+    LLB_CUDA_OK(err);
+  }
+  LLB_CUDA_OK(cudaGetLastError());
+  if (ctr) ctr->launches++;
+  return LLB_OK;
+}
+
 }  // namespace llb
 
 #ifdef LLB_GEMM_TRACE
@@ -573,4 +957,20 @@ extern "C" int llb_gemm_ln_residual(const void* A, int lda, const void* W, int l
   LLB_CHECK_ARG(A && W, "llb_gemm_ln_residual: null operand");
   llb::GemmLnArgs e{bias, row_group, shift, scale, gate, mod_ld, x, ldx, reinterpret_cast<__nv_bfloat16*>(xb), ldxb};
   return llb::launch_gemm_ln(A, lda, W, ldw, M, N, K, e, (cudaStream_t)stream, nullptr);
+}
+
+extern "C" int llb_gemm_ln_workspace_bytes(size_t* bytes) {
+  LLB_CHECK_ARG(bytes, "llb_gemm_ln_workspace_bytes: null argument");
+  *bytes = llb::gemm_ln_pair_workspace_bytes();
+  return LLB_OK;
+}
+
+extern "C" int llb_gemm_ln_residual_ws(const void* A, int lda, const void* W, int ldw, const float* bias, const int32_t* row_group,
+                                       const float* shift, const float* scale, const float* gate, int mod_ld, float* x, int ldx,
+                                       void* xb, int ldxb, int M, int N, int K, void* workspace, size_t workspace_bytes,
+                                       llb_stream_t stream) {
+  LLB_TRY(llb::require_sm100());
+  LLB_CHECK_ARG(A && W, "llb_gemm_ln_residual_ws: null operand");
+  llb::GemmLnArgs e{bias, row_group, shift, scale, gate, mod_ld, x, ldx, reinterpret_cast<__nv_bfloat16*>(xb), ldxb};
+  return llb::launch_gemm_ln_pair(A, lda, W, ldw, M, N, K, e, workspace, workspace_bytes, (cudaStream_t)stream, nullptr);
 }

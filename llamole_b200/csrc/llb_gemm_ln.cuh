@@ -28,6 +28,7 @@ constexpr int GLN_STAGES = 3;
 constexpr int GLN_STAGES = GLN_STAGES_OVERRIDE;
 #endif
 constexpr int GLN_MAX_CL = 4;
+constexpr int GLN_PAIR_MAX_GROUPS = 18;   // 4-pair groups of the CTA-pair variant (72 of the B200's 74 pairs)
 constexpr int GLN_MAX_GROUPS = 4;   // modulation rows staged per tile (a 128-row tile of 50-atom molecules touches <= 4)
 
 struct GemmLnArgs {
@@ -45,9 +46,15 @@ struct GemmLnArgs {
 
 // N must be CL * 256 with CL in 1..4 (hidden sizes 256 / 512 / 768 / 1024); callers fall back to GEMM + row kernel otherwise.
 inline bool gemm_ln_supported(int N, int K) { return N % GLN_BN == 0 && N / GLN_BN >= 1 && N / GLN_BN <= GLN_MAX_CL && K % 8 == 0; }
-int gemm_ln_mode();       // env LLB_FUSED_LN: 0 = GEMM + row kernel everywhere, 1 (default) = fuse the attention projection, 2 = fuse fc2 too
+int gemm_ln_mode();       // env LLB_FUSED_LN, 0..3 (default 3): see dit_forward
 inline bool gemm_ln_enabled() { return gemm_ln_mode() != 0; }
 int launch_gemm_ln(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const GemmLnArgs& e, cudaStream_t stream,
                    GemmCounters* ctr);
+
+// CTA-pair variant for N = 1024 (see llb_gemm_ln.cu): needs a caller-provided exchange workspace (any contents; the launch
+// clears its counters with a stream-ordered memset) that no other launch uses concurrently.
+size_t gemm_ln_pair_workspace_bytes();
+int launch_gemm_ln_pair(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const GemmLnArgs& e, void* sync_ws,
+                        size_t sync_bytes, cudaStream_t stream, GemmCounters* ctr);
 
 }  // namespace llb

@@ -52,8 +52,9 @@ def test_gemm_matches_torch(M, N, K, act, out_f32):
 
 # ------------------------------------------------------------------------------------------------ fused GEMM + LN tail
 @pytest.mark.parametrize("M,N,K,group_len", [(1, 256, 64, 50), (300, 1024, 1024, 50), (1000, 1024, 4096, 50), (777, 512, 256, 7),
-                                             (4097, 1024, 1024, 50), (260, 768, 768, 3), (128 * 41 + 5, 1024, 512, 50)])
-def test_gemm_ln_residual_matches_torch(M, N, K, group_len):
+                                             (4097, 1024, 1024, 50), (260, 768, 768, 3), (128 * 41 + 5, 1024, 512, 50), (256 * 40 + 130, 1024, 1024, 50)])
+@pytest.mark.parametrize("variant", ["cluster", "pair"])
+def test_gemm_ln_residual_matches_torch(M, N, K, group_len, variant):
     """x += gate * (LN(A W^T + b) (1 + scale) + shift) against fp32 torch; rows map to modulation rows in runs of
     `group_len` (3 and 7 force the more-than-4-groups-per-tile path), the last run is a shared 'unconditional' row."""
     g = torch.Generator(device="cpu").manual_seed(M + N + K)
@@ -70,9 +71,22 @@ def test_gemm_ln_residual_matches_torch(M, N, K, group_len):
     x = x0.clone()
     xb = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16)
     lib = _cabi.lib()
-    _cabi.check(lib.llb_gemm_ln_residual(_cabi.ptr(A), K, _cabi.ptr(W), K, _cabi.ptr(bias), _cabi.ptr(groups), _cabi.ptr(shift),
-                                         _cabi.ptr(scale), _cabi.ptr(gate), mod.shape[1], _cabi.ptr(x), N, _cabi.ptr(xb), N, M, N, K,
-                                         _cabi.stream_ptr()), "llb_gemm_ln_residual")
+    if variant == "pair":
+        if N != 1024:
+            pytest.skip("the CTA-pair variant is N = 1024 only")
+        import ctypes
+        nbytes = ctypes.c_size_t()
+        _cabi.check(lib.llb_gemm_ln_workspace_bytes(ctypes.byref(nbytes)))
+        ws = torch.full((nbytes.value,), 0x5A, device=DEV, dtype=torch.uint8)     # garbage: the launch clears what it needs
+        for _ in range(2):                                                        # twice on the same workspace
+            x.copy_(x0)
+            _cabi.check(lib.llb_gemm_ln_residual_ws(_cabi.ptr(A), K, _cabi.ptr(W), K, _cabi.ptr(bias), _cabi.ptr(groups), _cabi.ptr(shift),
+                                                    _cabi.ptr(scale), _cabi.ptr(gate), mod.shape[1], _cabi.ptr(x), N, _cabi.ptr(xb), N, M, N, K,
+                                                    _cabi.ptr(ws), nbytes.value, _cabi.stream_ptr()), "llb_gemm_ln_residual_ws")
+    else:
+        _cabi.check(lib.llb_gemm_ln_residual(_cabi.ptr(A), K, _cabi.ptr(W), K, _cabi.ptr(bias), _cabi.ptr(groups), _cabi.ptr(shift),
+                                             _cabi.ptr(scale), _cabi.ptr(gate), mod.shape[1], _cabi.ptr(x), N, _cabi.ptr(xb), N, M, N, K,
+                                             _cabi.stream_ptr()), "llb_gemm_ln_residual")
     torch.cuda.synchronize()
     y = (A.double() @ W.double().t() + bias.double())
     ln = torch.nn.functional.layer_norm(y, (N,), eps=1e-5)

@@ -20,19 +20,22 @@ int main() {
   cudaMemcpy(grp, g.data(), M * 4, cudaMemcpyHostToDevice);
   long long* trace;
   cudaMalloc(&trace, 64 * 16 * 8);
+  void* ws; const size_t wsb = gemm_ln_pair_workspace_bytes(); cudaMalloc(&ws, wsb);
   const int nexp = 6;
-  const int exps[nexp] = {0, 1, 2, 3, 4, 7};
+  const int exps[nexp] = {0, 3, 4, 7, 8, 16};
+  for (int pairmode = 1; pairmode < 2; ++pairmode)
   for (int xi = 0; xi < nexp; ++xi)
   for (int K : {1024, 4096}) {
     llb_gln_set_exp(exps[xi]);
-    printf("=== exp mask %d (1 no x store, 2 no xb store, 4 no residual reload)\n", exps[xi]);
+    printf("=== %s kernel, knock-out mask %d (1 no x store, 2 no xb store, 4 no residual reload, 8 no pass 2, 16 empty epilogue)\n", pairmode ? "pair" : "cluster", exps[xi]);
     GemmLnArgs e{bias, grp, mod, mod + N, mod + 2 * N, 6 * N, x, N, xb, N};
+    auto launch = [&]() { return pairmode ? launch_gemm_ln_pair(A, K, W, K, M, N, K, e, ws, wsb, 0, nullptr) : launch_gemm_ln(A, K, W, K, M, N, K, e, 0, nullptr); };
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0), cudaEventCreate(&e1);
     for (int i = 0; i < 2; ++i)
-      if (launch_gemm_ln(A, K, W, K, M, N, K, e, 0, nullptr)) { printf("launch failed: %s\n", llb_last_error()); return 1; }
+      if (launch()) { printf("launch failed: %s\n", llb_last_error()); return 1; }
     cudaEventRecord(e0);
-    for (int i = 0; i < 10; ++i) launch_gemm_ln(A, K, W, K, M, N, K, e, 0, nullptr);
+    for (int i = 0; i < 10; ++i) launch();
     cudaEventRecord(e1);
     cudaDeviceSynchronize();
     float ms;
@@ -41,14 +44,14 @@ int main() {
     printf("K=%d: %.3f ms  %.0f TFLOP/s  (%s)\n", K, ms, 2.0 * M * N * K / ms / 1e9, cudaGetErrorString(cudaGetLastError()));
     cudaMemset(trace, 0, 64 * 16 * 8);
     llb_gln_set_trace(trace);
-    launch_gemm_ln(A, K, W, K, M, N, K, e, 0, nullptr);
+    launch();
     cudaDeviceSynchronize();
     llb_gln_set_trace(nullptr);
     std::vector<long long> h(64 * 16);
     cudaMemcpy(h.data(), trace, h.size() * 8, cudaMemcpyDeviceToHost);
     auto T = [&](int t, int s) { return h[(size_t)t * 16 + s]; };
     printf("tile | epi: phaseA  wait_tmem  pass1  stats_wait  pass2  period | mma: wait_empty  span | pass2: tmem  math+sts  res_wait  coalesced\n");
-    for (int t = 5; t < 8; ++t)
+    for (int t = 6; t < 8; ++t)
       printf("%3d | %6lld %6lld %6lld %6lld %6lld %6lld | %6lld %6lld | %6lld %6lld %6lld %6lld\n", t, T(t, 1) - T(t, 0), T(t, 2) - T(t, 1), T(t, 3) - T(t, 2),
              T(t, 4) - T(t, 3), T(t, 5) - T(t, 4), T(t, 0) - T(t - 1, 0), T(t, 9) - T(t, 8), T(t, 10) - T(t, 9), T(t, 11), T(t, 12), T(t, 13), T(t, 14));
   }
