@@ -97,6 +97,28 @@ __device__ __forceinline__ float gelu_fast(float x) {
   p = fmaf(p, a, -1.0000376025053335f);
   return fmaf(-a, ex2_approx(p), fmaxf(x, 0.0f));
 }
+// Same function with 2^p evaluated on the FMA pipe (round-to-nearest split p = i + f, degree-4 polynomial for 2^f,
+// exponent add), i.e. no MUFU instruction at all: 16 FP32/INT instructions instead of 8 + 1 MUFU.  Max |error| vs the
+// fp64 erf form 1.1e-6.  Used where the MUFU / MIO queue is the scarcer resource (see the fc1 epilogue notes in DESIGN.md).
+__device__ __forceinline__ float gelu_fma_only(float x) {
+  const float a = fabsf(x);
+  float p = -0.0004733077904837858f;
+  p = fmaf(p, a, 0.007084582472665392f);
+  p = fmaf(p, a, -0.05182752433176751f);
+  p = fmaf(p, a, -0.45999221096226367f);
+  p = fmaf(p, a, -1.150787981711536f);
+  p = fmaf(p, a, -1.0000376025053335f);
+  p = fmaxf(p, -125.0f);
+  const float t = p + 12582912.0f;                  // 1.5 * 2^23: the integer part of p lands in the low mantissa bits
+  const float f = p - (t - 12582912.0f);            // in [-0.5, 0.5]
+  float e = 0.009570098074450925f;
+  e = fmaf(e, f, 0.05591786664763956f);
+  e = fmaf(e, f, 0.24024744980255675f);
+  e = fmaf(e, f, 0.6931218139887697f);
+  e = fmaf(e, f, 0.9999992613818445f);
+  const float h = __int_as_float(__float_as_int(e) + (__float_as_int(t) << 23));   // e * 2^i (the magic constant's bits shift out)
+  return fmaf(-a, h, fmaxf(x, 0.0f));
+}
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 __device__ __forceinline__ float softsign(float x) { return x / (1.0f + fabsf(x)); }
 
@@ -142,6 +164,22 @@ __device__ __forceinline__ float exp1_from_bits(uint32_t bits) {
 // ------------------------------------------------------------------------------------------------
 // sm_100a PTX wrappers: mbarrier, TMA, tcgen05 / TMEM
 // ------------------------------------------------------------------------------------------------
+// Warp index as a value the compiler KNOWS to be warp-uniform (a shuffle result), so that the role branches are uniform
+// branches and everything a role derives from kernel arguments, loop counters and shared-memory bases stays in uniform
+// registers.  Without it every tcgen05.mma / tcgen05.commit / TMA issue is wrapped in an ELECT + R2UR waterfall loop
+// (~20 extra instructions each), which made the single MMA-issuing thread nearly as slow as the tensor pipe itself.
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+// One elected lane of a converged warp (deterministic: the same lane every time, as tcgen05.commit requires).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -73,7 +73,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const Epi& epi, const CUtenso
   constexpr int ROW_BYTES = Epi::CHUNK * ELEM;
   constexpr int NBUF = GEMM_STAGING_PER_WARP / (32 * ROW_BYTES);
   constexpr int COLS_PER_WARP = BN / (GEMM_EPI_WARPS / 4);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int quarter = warp & 3, cg = warp >> 2;
   const int row = m0 + quarter * 32 + lane;
   const uint32_t t_row = tmem_acc + ((uint32_t)(quarter * 32) << 16) + cg * COLS_PER_WARP;
@@ -89,7 +89,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const Epi& epi, const CUtenso
     if (LLB_EXP(8)) continue;
     if (TMA_STORE) {
       uint8_t* dst = stg + buf * (32 * ROW_BYTES);
-      if (lane == 0) bulk_wait_read<NBUF - 1>();   // the buffer about to be overwritten has been read out
+      if (elect_one()) bulk_wait_read<NBUF - 1>();   // the buffer about to be overwritten has been read out
       __syncwarp();
       // row `lane` of the staging tile, 16-byte pieces XOR-swizzled exactly like the C tensor map
       uint8_t* rowp = dst + lane * ROW_BYTES;
@@ -108,7 +108,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const Epi& epi, const CUtenso
       }
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) {
+      if (elect_one()) {
         tma_store_2d(tmC, dst, col0, m0 + quarter * 32);
         bulk_commit();
       }
@@ -154,14 +154,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
   const int num_m = (M + GEMM_BM - 1) / GEMM_BM;
   const int num_n = (N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
   const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
 
-  if (warp == GEMM_EPI_WARPS && lane == 0) {
+  if (warp == GEMM_EPI_WARPS && elect_one()) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (TMA_STORE) tma_prefetch_desc(&tmC);
@@ -182,58 +182,60 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == GEMM_EPI_WARPS) {
-    // ---------------- TMA producer ----------------
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / num_n) * GEMM_BM;
-        const int n0 = (tile % num_n) * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
+    // ---------------- TMA producer: the whole warp walks the ring (uniform control flow), one elected lane issues ----------------
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / num_n) * GEMM_BM;
+      const int n0 = (tile % num_n) * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
           tma_load_2d(smA + stage * Cfg::A_BYTES, &tmA, &full[stage], kb * GEMM_BK, m0);
           tma_load_2d(smB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * GEMM_BK, n0);
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
   } else if (warp == GEMM_EPI_WARPS + 1) {
-    // ---------------- MMA issuer ----------------
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+    // ---------------- MMA issuer: converged warp, one elected lane issues (operands stay in uniform registers) ----------------
+    constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
+    const uint64_t a_desc0 = umma_desc_k128(smem_u32(smA));   // stage 0, k-step 0; stages / k-steps are plain adds
+    const uint64_t b_desc0 = umma_desc_k128(smem_u32(smB));
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smA + stage * Cfg::A_BYTES);
-          const uint32_t b_addr = smem_u32(smB + stage * Cfg::B_BYTES);
+        if (elect_one()) {
+          const uint64_t a_desc = a_desc0 + (uint64_t)(stage * (Cfg::A_BYTES >> 4));
+          const uint64_t b_desc = b_desc0 + (uint64_t)(stage * (Cfg::B_BYTES >> 4));
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) {
-            umma_bf16(d_tmem, umma_desc_k128(a_addr + k * 32), umma_desc_k128(b_addr + k * 32), idesc,
-                      (kb | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < GEMM_BK / 16; ++k) umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit(&empty[stage]);
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
         }
-        umma_commit(&tmem_full[acc]);
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1;
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
+      }
+      if (elect_one()) umma_commit(&tmem_full[acc]);
+      __syncwarp();
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
       }
     }
   } else if (warp < GEMM_EPI_WARPS) {
@@ -344,7 +346,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
@@ -353,7 +355,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   const int num_tiles = num_m * num_n;
   const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
 
-  if (warp == GEMM_EPI_WARPS && lane == 0) {
+  if (warp == GEMM_EPI_WARPS && elect_one()) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (TMA_STORE) tma_prefetch_desc(&tmC);
@@ -380,46 +382,51 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
   if (warp == GEMM_EPI_WARPS) {
     // ---------------- TMA producer (both CTAs; completion bytes go to the leader's full[]) ----------------
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int tcount = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++tcount) {
-        const int m0 = (tile / num_n) * (2 * GEMM_BM) + rank * GEMM_BM;
-        const int n0 = (tile % num_n) * BN + rank * (BN / 2);
-        long long wsum = 0;
-        for (int kb = 0; kb < num_kb; ++kb) {
+    // the whole warp walks the ring (uniform control flow); one elected lane issues
+    int stage = 0;
+    uint32_t phase = 0;
+    int tcount = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++tcount) {
+      const int m0 = (tile / num_n) * (2 * GEMM_BM) + rank * GEMM_BM;
+      const int n0 = (tile % num_n) * BN + rank * (BN / 2);
+      long long wsum = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
 #ifdef LLB_GEMM_TRACE
-          const long long w0 = clock64();
+        const long long w0 = clock64();
 #endif
-          mbar_wait(&empty[stage], phase ^ 1);
+        mbar_wait(&empty[stage], phase ^ 1);
 #ifdef LLB_GEMM_TRACE
-          wsum += clock64() - w0;
-          if (kb == num_kb - 1) { LLB_TRACE(tcount, 0, wsum); LLB_TRACE(tcount, 1, clock64()); }
+        wsum += clock64() - w0;
+        if (kb == num_kb - 1 && lane == 0) { LLB_TRACE(tcount, 0, wsum); LLB_TRACE(tcount, 1, clock64()); }
 #endif
+        if (elect_one()) {
           if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
           tma_load_2d_2sm(smA + stage * Cfg::A_BYTES, &tmA, &full[stage], kb * GEMM_BK, m0);
           tma_load_2d_2sm(smB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * GEMM_BK, n0);
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
       }
+      (void)wsum;
     }
   } else if (warp == GEMM_EPI_WARPS + 1) {
-    // ---------------- MMA issuer (leader CTA only) ----------------
-    if (rank == 0 && lane == 0) {
+    // ---------------- MMA issuer (leader CTA only): converged warp, one elected lane issues ----------------
+    if (rank == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(2 * GEMM_BM, BN);
+      const uint64_t a_desc0 = umma_desc_k128(smem_u32(smA));   // stage 0, k-step 0; stages / k-steps are plain adds
+      const uint64_t b_desc0 = umma_desc_k128(smem_u32(smB));
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       int tcount = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs, ++tcount) {
-        LLB_TRACE(tcount, 2, clock64());
+        if (lane == 0) LLB_TRACE(tcount, 2, clock64());
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-        LLB_TRACE(tcount, 3, clock64());
+        if (lane == 0) LLB_TRACE(tcount, 3, clock64());
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         long long fsum = 0;
@@ -430,24 +437,27 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           mbar_wait(&full[stage], phase);
 #ifdef LLB_GEMM_TRACE
           fsum += clock64() - w0;
-          if (kb == num_kb - 1) { LLB_TRACE(tcount, 4, fsum); LLB_TRACE(tcount, 5, clock64()); }
+          if (kb == num_kb - 1 && lane == 0) { LLB_TRACE(tcount, 4, fsum); LLB_TRACE(tcount, 5, clock64()); }
 #endif
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smA + stage * Cfg::A_BYTES);
-          const uint32_t b_addr = smem_u32(smB + stage * Cfg::B_BYTES);
+          if (elect_one()) {
+            const uint64_t a_desc = a_desc0 + (uint64_t)(stage * (Cfg::A_BYTES >> 4));
+            const uint64_t b_desc = b_desc0 + (uint64_t)(stage * (Cfg::B_BYTES >> 4));
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) {
-            if (!LLB_EXP(1))
-              umma_bf16_2sm(d_tmem, umma_desc_k128(a_addr + k * 32), umma_desc_k128(b_addr + k * 32), idesc,
-                            (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < GEMM_BK / 16; ++k) {
+              if (!LLB_EXP(1)) umma_bf16_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit_2sm(&empty[stage]);
           }
-          umma_commit_2sm(&empty[stage]);
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit_2sm(&tmem_full[acc]);
+        if (elect_one()) umma_commit_2sm(&tmem_full[acc]);
+        __syncwarp();
+        (void)fsum;
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -563,6 +573,13 @@ int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, in
 template <int ACT>
 __device__ __forceinline__ float apply_act(float x) {
   if (ACT == LLB_ACT_GELU) return gelu_fast(x);
+  if (ACT == 9) return gelu_fma_only(x);   // experiment variants (tools/gemm_trace.cu only)
+  if (ACT == 10) {
+    float y = x;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) y = fmaf(y, 0.999f, 0.001f);
+    return y;
+  }
   if (ACT == LLB_ACT_SILU) return silu(x);
   if (ACT == LLB_ACT_SOFTSIGN) return softsign(x);
   return x;

@@ -137,7 +137,7 @@ __device__ __forceinline__ void gln_pass2(const GlnPass2& a, const CUtensorMap* 
       v[4 * p + 3] = fmaf(fmaf(v[4 * p + 3] + b.w, a.rstd, a.nmr), s1.w, sh.w);
     }
     // the staging tiles are free once the previous chunk's TMA stores have read them
-    if (lane == 0) bulk_wait_read<0>();
+    if (elect_one()) bulk_wait_read<0>();
     __syncwarp();
 #pragma unroll
     for (int p = 0; p < 8; ++p) sts128(wr + ((p ^ (lane & 7)) << 4), make_float4(v[4 * p], v[4 * p + 1], v[4 * p + 2], v[4 * p + 3]));
@@ -164,7 +164,7 @@ __device__ __forceinline__ void gln_pass2(const GlnPass2& a, const CUtensorMap* 
     }
     fence_proxy_async_smem();
     __syncwarp();
-    if (lane == 0) {
+    if (elect_one()) {
       if (!GLN_EXP(1)) tma_store_2d(tmX, reinterpret_cast<const void*>(__cvta_shared_to_generic(a.xstg)), a.gcol + c, a.grow);
       if (!GLN_EXP(2)) tma_store_2d(tmXb, reinterpret_cast<const void*>(__cvta_shared_to_generic(a.xbstg)), a.gcol + c, a.grow);
       bulk_commit();
@@ -293,7 +293,7 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   uint64_t* mod_empty = bars + 2 * STAGES + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 10);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_rank();
   const int cluster_id = blockIdx.x / CL, num_clusters = gridDim.x / CL;
@@ -302,7 +302,7 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const int n0 = (int)rank * BN;
   const int N = CL * BN;
 
-  if (warp == GEMM_EPI_WARPS && lane == 0) {
+  if (warp == GEMM_EPI_WARPS && elect_one()) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmX);
@@ -330,59 +330,63 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == GEMM_EPI_WARPS) {
-    // ---------------- TMA producer ----------------
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int mt = cluster_id; mt < num_m; mt += num_clusters) {
-        const int m0 = mt * GEMM_BM;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
+    // ---------------- TMA producer (converged warp, one elected lane issues) ----------------
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int mt = cluster_id; mt < num_m; mt += num_clusters) {
+      const int m0 = mt * GEMM_BM;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(&full[stage], S::STAGE_BYTES);
           tma_load_2d(smA + stage * S::A_BYTES, &tmA, &full[stage], kb * GEMM_BK, m0);
           tma_load_2d(smB + stage * S::B_BYTES, &tmB, &full[stage], kb * GEMM_BK, n0);
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
   } else if (warp == GEMM_EPI_WARPS + 1) {
-    // ---------------- MMA issuer ----------------
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      int tcount = 0;
-      for (int mt = cluster_id; mt < num_m; mt += num_clusters, ++tcount) {
-        GLN_TRACE(tcount, 8, clock64());
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-        GLN_TRACE(tcount, 9, clock64());
+    // ---------------- MMA issuer (converged warp, one elected lane issues; operands in uniform registers) ----------------
+    constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
+    const uint64_t a_desc0 = umma_desc_k128(smem_u32(smA));
+    const uint64_t b_desc0 = umma_desc_k128(smem_u32(smB));
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int tcount = 0;
+    for (int mt = cluster_id; mt < num_m; mt += num_clusters, ++tcount) {
+      if (lane == 0) GLN_TRACE(tcount, 8, clock64());
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      if (lane == 0) GLN_TRACE(tcount, 9, clock64());
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smA + stage * S::A_BYTES);
-          const uint32_t b_addr = smem_u32(smB + stage * S::B_BYTES);
+        if (elect_one()) {
+          const uint64_t a_desc = a_desc0 + (uint64_t)(stage * (S::A_BYTES >> 4));
+          const uint64_t b_desc = b_desc0 + (uint64_t)(stage * (S::B_BYTES >> 4));
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k)
-            umma_bf16(d_tmem, umma_desc_k128(a_addr + k * 32), umma_desc_k128(b_addr + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < GEMM_BK / 16; ++k) umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit(&empty[stage]);
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
         }
-        umma_commit(&tmem_full[acc]);
-        GLN_TRACE(tcount, 10, clock64());
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1;
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
+      }
+      if (elect_one()) umma_commit(&tmem_full[acc]);
+      __syncwarp();
+      if (lane == 0) GLN_TRACE(tcount, 10, clock64());
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
       }
     }
   } else if (warp == GEMM_EPI_WARPS + 3) {
@@ -578,13 +582,13 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* mod_empty = bars + 2 * STAGES + 6;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 8);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
   const int num_mb = (M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
   const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
   const int n0 = slice * BN;
 
-  if (warp == GEMM_EPI_WARPS && lane == 0) {
+  if (warp == GEMM_EPI_WARPS && elect_one()) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmBh);
     tma_prefetch_desc(&tmX);
@@ -616,55 +620,61 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == GEMM_EPI_WARPS) {
     // ---------------- TMA producer (both CTAs; completion bytes go to the leader's full[]) ----------------
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const int nB = n0 + (int)rank * (BN / 2);
-      for (int mb = grp; mb < num_mb; mb += G) {
-        const int m0 = mb * 2 * GEMM_BM + (int)rank * GEMM_BM;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    const int nB = n0 + (int)rank * (BN / 2);
+    for (int mb = grp; mb < num_mb; mb += G) {
+      const int m0 = mb * 2 * GEMM_BM + (int)rank * GEMM_BM;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one()) {
           if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * S::STAGE_BYTES);
           tma_load_2d_2sm(smA + stage * S::A_BYTES, &tmA, &full[stage], kb * GEMM_BK, m0);
           tma_load_2d_2sm(smB + stage * S::B_BYTES, &tmBh, &full[stage], kb * GEMM_BK, nB);
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
   } else if (warp == GEMM_EPI_WARPS + 1) {
-    // ---------------- MMA issuer (leader CTA only) ----------------
-    if (rank == 0 && lane == 0) {
+    // ---------------- MMA issuer (leader CTA only; converged warp, one elected lane issues) ----------------
+    if (rank == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(2 * GEMM_BM, BN);
+      const uint64_t a_desc0 = umma_desc_k128(smem_u32(smA));
+      const uint64_t b_desc0 = umma_desc_k128(smem_u32(smB));
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       int tcount = 0;
       for (int mb = grp; mb < num_mb; mb += G, ++tcount) {
-        GLN_TRACE(tcount, 8, clock64());
+        if (lane == 0) GLN_TRACE(tcount, 8, clock64());
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-        GLN_TRACE(tcount, 9, clock64());
+        if (lane == 0) GLN_TRACE(tcount, 9, clock64());
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smA + stage * S::A_BYTES);
-          const uint32_t b_addr = smem_u32(smB + stage * S::B_BYTES);
+          if (elect_one()) {
+            const uint64_t a_desc = a_desc0 + (uint64_t)(stage * (S::A_BYTES >> 4));
+            const uint64_t b_desc = b_desc0 + (uint64_t)(stage * (S::B_BYTES >> 4));
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k)
-            umma_bf16_2sm(d_tmem, umma_desc_k128(a_addr + k * 32), umma_desc_k128(b_addr + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit_2sm(&empty[stage]);
+            for (int k = 0; k < GEMM_BK / 16; ++k) umma_bf16_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_2sm(&empty[stage]);
+          }
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit_2sm(&tmem_full[acc]);
-        GLN_TRACE(tcount, 10, clock64());
+        if (elect_one()) umma_commit_2sm(&tmem_full[acc]);
+        __syncwarp();
+        if (lane == 0) GLN_TRACE(tcount, 10, clock64());
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;

@@ -12,6 +12,8 @@ static float* bias;
 
 static int run(int M, int N, int K, int act) {
   if (act == 1) return launch_gemm<256>(A, K, W, K, M, N, K, EpiBiasAct<LLB_ACT_GELU, false>{C, N, bias}, 0);
+  if (act == 9) return launch_gemm<256>(A, K, W, K, M, N, K, EpiBiasAct<9, false>{C, N, bias}, 0);
+  if (act == 10) return launch_gemm<256>(A, K, W, K, M, N, K, EpiBiasAct<10, false>{C, N, bias}, 0);
   return launch_gemm<256>(A, K, W, K, M, N, K, EpiBiasAct<LLB_ACT_NONE, false>{C, N, bias}, 0);
 }
 
@@ -34,8 +36,8 @@ int main(int argc, char** argv) {
   cudaMalloc(&A, maxMK * 2), cudaMalloc(&W, (size_t)4096 * 4096 * 2), cudaMalloc(&C, maxMK * 2), cudaMalloc(&bias, 4096 * 4);
   cudaMemset(A, 0x11, maxMK * 2), cudaMemset(W, 0x11, (size_t)4096 * 4096 * 2), cudaMemset(bias, 0, 4096 * 4);
   struct Shape { const char* name; int M, N, K, act; };
-  const Shape shapes[] = {{"fc1", 204800, 4096, 1024, 1}, {"fc1-noact", 204800, 4096, 1024, 0}, {"fc2", 204800, 1024, 4096, 0},
-                          {"proj", 204800, 1024, 1024, 0}, {"qkv-plain", 204800, 3072, 1024, 0}};
+  const Shape shapes[] = {{"fc1", 204800, 4096, 1024, 1}, {"fc1-nomufu", 204800, 4096, 1024, 9}, {"fc1-8ffma", 204800, 4096, 1024, 10},
+                          {"fc1-noact", 204800, 4096, 1024, 0}, {"fc2", 204800, 1024, 4096, 0}};
   const int masks[] = {0, 4, 8, 12, 2, 1, 3};
   const char* mask_name[] = {"full", "no-math", "no-store", "ld-only-epi", "no-epilogue", "no-mma", "loads-only"};
   printf("%-10s", "shape");
