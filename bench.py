@@ -219,6 +219,8 @@ def workload_config(args):
         "dit": {"hidden": DIT["hidden"], "depth": DIT["depth"], "heads": DIT["heads"], "max_nodes": DIT["max_nodes"],
                 "timesteps": DIT["T"], "guide_scale": DIT["guide_scale"], "batch_per_gpu": args.dit_batch, "weights": "random-init"},
         "gin_workload": "BASELINE.json configs[1]: GraphCLIP (GIN, H=768, L=5) forward over %d synthetic molecular graphs per GPU" % args.gin_graphs,
+        "predictor_workload": "BASELINE.json configs[3]: A* candidate scoring, GIN predictor (H=768, L=5, %d templates) + top-50 over %d synthetic "
+                              "reactant graphs per GPU (64k graphs batch-sharded over 8 GPUs)" % (args.pred_out_dim, args.pred_graphs),
         "l2": "activations per step (~7 GB) and GIN node matrices (~375 MB) exceed the 126 MB L2; no explicit flush",
         "parallelism": "dp%d (independent molecule/graph shards, one NCCL all-gather of results)" % args.gpus,
     }
@@ -233,6 +235,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--dit-batch", type=int, default=2048)
     ap.add_argument("--gin-graphs", type=int, default=4096)
+    ap.add_argument("--pred-graphs", type=int, default=8192, help="A* candidate scoring: reactant graphs per GPU (BASELINE.json configs[3]: 64k over 8 GPUs)")
+    ap.add_argument("--pred-out-dim", type=int, default=180576)
+    ap.add_argument("--no-predictor", action="store_true")
     ap.add_argument("--small", action="store_true", help="tiny model (debug only; invalid as a benchmark)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -342,6 +347,9 @@ def main():
     del X, E
     # ------------------------------------------------------------------ GIN encoder
     gin = bench_gin(args, device, rank, world, barrier, max_over_ranks, pk)
+    pred = None
+    if not args.no_predictor and not args.small:
+        pred = bench_predictor(args, device, rank, world, barrier, max_over_ranks, pk)
     # ------------------------------------------------------------------ CPU baseline (rank 0, N=1)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.small:
@@ -357,8 +365,8 @@ def main():
             "metric": METRIC, "value": value, "unit": "molecules/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic", "config": workload_config(args), "clocks": clocks.summary(), "e2e": e2e,
-            "gpu_launches": int(dit_launches + gin.pop("_launches")), "roofline": roofline, "cpu_baseline": cpu,
-            "kernel_breakdown": breakdown, "gin": gin,
+            "gpu_launches": int(dit_launches + gin.pop("_launches") + (pred.pop("_launches") if pred else 0)), "roofline": roofline,
+            "cpu_baseline": cpu, "kernel_breakdown": breakdown, "gin": gin, "predictor": pred,
         }
         print(json.dumps(out), flush=True)
     if world > 1:
@@ -373,6 +381,85 @@ def gin_cpu_baseline(gin):
     sec = cpu_gin_seconds(enc, proj, graphs)
     return {"value": 512 / sec, "unit": "graphs/s", "cores": torch.get_num_threads(), "kind": "port",
             "sample": "first 512 of the 4096 graphs, one GraphCLIP forward, oracle/llamole_oracle.py in fp32"}
+
+
+def bench_predictor(args, device, rank, world, barrier, max_over_ranks, pk):
+    """BASELINE.json configs[3]: reaction-template predictor (GIN trunk with text adapters + 4H head over out_dim templates)
+    with the fused softmax/top-50, graphs resident in HBM; weak scaling (the same number of graphs on every GPU)."""
+    from llamole_b200 import GraphPredictor, _cabi, synth
+
+    H, L, D, k = GIN["hidden"], GIN["layers"], args.pred_out_dim, 50
+    t0 = time.time()
+    sd = synth.gin_predictor_state_dict(L, H, D, seed=13)
+    m = GraphPredictor(L, H, 0.0, D, {"text_input_size": synth.TEXT_DIM}, {}, None)
+    m.predictor.load_state_dict(sd)
+    m.disable_grads()
+    m = m.to(device)
+    del sd
+    G = args.pred_graphs
+    x, ei, ea, batch = synth.molecular_graphs(G, seed=100 + rank)
+    c = synth.text_conditions(G, seed=7 + rank).to(device)
+    xd, eid, ead, bd = (t.to(device) for t in (x, ei, ea, batch))
+    n, e = int(x.numel()), int(ea.numel())
+    eng = m.engine()
+    log(f"predictor set-up took {time.time() - t0:.1f}s")
+    iters = 5
+    for _ in range(3):
+        eng.bind(xd, eid, ead, bd, num_graphs=G, want_logits=True)
+        probs, idx = eng.predictor_topk(c, k)
+    barrier()
+    l0 = eng.launch_count()
+    _cabi.profile_enable(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(iters):
+        eng.bind(xd, eid, ead, bd, num_graphs=G, want_logits=True)
+        probs, idx = eng.predictor_topk(c, k)
+    if world > 1:   # the one exchange of the path: gather the candidates' top-k
+        import torch.distributed as dist
+
+        gp = [torch.empty_like(probs) for _ in range(world)]
+        gi = [torch.empty_like(idx) for _ in range(world)]
+        dist.all_gather(gp, probs)
+        dist.all_gather(gi, idx)
+    ev1.record()
+    barrier()
+    ms = max_over_ranks(ev0.elapsed_time(ev1)) / iters
+    prof = _cabi.profile_read()
+    _cabi.profile_enable(False)
+    launches = eng.launch_count() - l0
+    # e2e: host graphs + conditions -> top-k on the host
+    xp, eip, eap, bp, cp = (t.pin_memory() for t in (x, ei, ea, batch, c.cpu()))
+    hp = torch.empty((G, k), dtype=torch.float32).pin_memory()
+    hi = torch.empty((G, k), dtype=torch.int32).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        pr, ix = m.topk_templates(xp.to(device, non_blocking=True), eip.to(device, non_blocking=True), eap.to(device, non_blocking=True),
+                                  bp.to(device, non_blocking=True), cp.to(device, non_blocking=True), k)
+        hp.copy_(pr, non_blocking=True)
+        hi.copy_(ix, non_blocking=True)
+        torch.cuda.synchronize()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / reps)
+    trunk_flops = 16.0 * n * H * H * L + 16.0 * H * H * (L - 1) * G + 2.0 * G * 768 * 3 * H * L
+    head_flops = (8.0 * H * H + 8.0 * H * D) * G
+    head_ms = prof.get("gin_gemm_head", (0.0, 0))[0] / iters
+    out = {
+        "value": world * G / (ms / 1e3), "unit": "graphs/s", "ms_per_batch": ms, "graphs_per_gpu": G, "nodes": n, "directed_edges": e,
+        "config": {"hidden": H, "layers": L, "out_dim": D, "topk": k,
+                   "timed": "CSR build + predictor trunk + head + softmax/top-50, inputs resident in HBM" + (", + all_gather of the top-k" if world > 1 else "")},
+        "e2e": {"value": world * G / (e2e_ms / 1e3), "unit": "graphs/s", "h2d_bytes_per_step": (n * 2 + e * 3) * 8 + G * 768 * 4,
+                "d2h_bytes_per_step": G * k * 8},
+        "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05 (predictor head, 4H x out_dim)", "achieved": head_flops / (head_ms / 1e3) / 1e12 if head_ms else None,
+                     "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": head_flops / (head_ms / 1e3) / 1e12 / pk["tf_sustained"] if head_ms else None,
+                     "traffic": None, "peak_source": pk["source"], "flops_per_batch": head_flops, "whole_batch_tflops": (trunk_flops + head_flops) / (ms / 1e3) / 1e12},
+        "kernel_breakdown": {k_: {"ms_per_batch": v[0] / iters, "launches": v[1] / iters} for k_, v in prof.items() if k_.startswith("gin_")},
+        "_launches": launches,
+    }
+    del m, eng
+    torch.cuda.empty_cache()
+    return out
 
 
 def bench_gin(args, device, rank, world, barrier, max_over_ranks, pk):

@@ -538,6 +538,7 @@ int llb_dit_begin(llb_dit* h, void* workspace, size_t workspace_bytes, int B, co
     LLB_CUDA_OK(cudaMemcpyAsync(h->row_mol, row_mol.data(), (size_t)Mtok * 4, cudaMemcpyHostToDevice, s));
     LLB_CUDA_OK(cudaMemcpyAsync(h->row_group, row_group.data(), (size_t)h->passes * Mtok * 4, cudaMemcpyHostToDevice, s));
   }
+  LLB_CUDA_OK(cudaMemsetAsync(h->ln_sync, 0, gemm_ln_pair_workspace_bytes(), s));   // mailbox tags start from a known state
   // the copies above read pageable host memory: they have been staged by the time cudaMemcpyAsync returns
   dit_cond_operand_kernel<<<dim3(B, L.ydim + 1), 256, 0, s>>>(props, txt, h->w<float>(L.y_mlp0_w), h->w<float>(L.y_mlp0_b), h->acond,
                                                               h->missing, L.ydim, L.tdim, L.H, L.KC);

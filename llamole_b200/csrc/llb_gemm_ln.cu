@@ -1,6 +1,8 @@
 // Cluster GEMM with the LayerNorm / adaLN-modulate / gate / residual tail fused into the epilogue (see llb_gemm_ln.cuh).
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "llb_gemm_ln.cuh"
 
 namespace llb {
@@ -544,17 +546,24 @@ struct GlnPairSmem {
 };
 static_assert(GlnPairSmem::TOTAL <= 232448, "gemm_ln pair kernel shared memory exceeds the 227 KB per-CTA limit");
 
-__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+// Statistics mailbox entry: {sum, tag, sum of squares, tag}.  Data and flag travel in the same 8-byte halves (each
+// half is an atomic access), so the exchange needs no fence, no atomic and no counter: a reader simply re-reads until both
+// tags carry the value expected for this launch and tile.
+__device__ __forceinline__ void st_mailbox(uint4* p, float s, float ss, uint32_t tag) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(__float_as_uint(s)), "r"(tag), "r"(__float_as_uint(ss)), "r"(tag)
+               : "memory");
+}
+__device__ __forceinline__ uint4 ld_mailbox(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
                     const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXb,
-                    const __grid_constant__ CUtensorMap tmXpf, int M, int K, int G, GemmLnArgs e, uint32_t* sync_cnt,
-                    float2* sync_stats) {
+                    const __grid_constant__ CUtensorMap tmXpf, int M, int K, int G, GemmLnArgs e, uint4* sync_stats,
+                    uint32_t tag_base) {
   using S = GlnPairSmem;
   constexpr int STAGES = S::STAGES;
   constexpr int BN = GLN_BN;
@@ -708,7 +717,6 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     a.bias_s = smem_u32(biasS + cbase);
     a.xstride = (size_t)4 * e.ldx;
     a.gcol = n0 + cbase;
-    uint32_t* my_cnt = sync_cnt + (size_t)(grp * 2 + rank) * 32;   // one 128-byte line per (group, rank)
     int acc = 0;
     uint32_t acc_phase = 0;
     int tcount = 0;
@@ -739,16 +747,12 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       partS[ch * GEMM_BM + rloc] = gln_pass1(a.t_row, a.bias_s);
       epi_bar_sync();
-      // statistics slots: [group][tile parity][rank][slice][128 rows]
-      float2* gstats = sync_stats + (size_t)((grp * 2 + (tcount & 1)) * 2 + rank) * NS * GEMM_BM;
+      // statistics mailboxes: [group][tile parity][rank][slice][128 rows]
+      uint4* gstats = sync_stats + (size_t)((grp * 2 + (tcount & 1)) * 2 + rank) * NS * GEMM_BM;
+      const uint32_t tag = tag_base + (uint32_t)(tcount + 1);
       if (ch == 0) {
         const float2 p0 = partS[rloc], p1 = partS[GEMM_BM + rloc];
-        gstats[slice * GEMM_BM + rloc] = make_float2(p0.x + p1.x, p0.y + p1.y);
-        __syncwarp();
-        if (lane == 0) {
-          __threadfence();
-          atomicAdd(my_cnt, 1u);
-        }
+        st_mailbox(gstats + slice * GEMM_BM + rloc, p0.x + p1.x, p0.y + p1.y, tag);
       }
       if (tr) GLN_TRACE(tcount, 3, clock64());
       // first residual chunk: in flight while the statistics travel
@@ -760,26 +764,28 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
       for (int it = 0; it < 8; ++it)
         res[it] = (it * 4 < a.rows_left) ? *reinterpret_cast<const float4*>(a.xrow + it * a.xstride) : make_float4(0.f, 0.f, 0.f, 0.f);
-      // all four slices of this rank have published tile `tcount`: 4 CTAs x 4 statistics warps each
-      if (lane == 0) {
-        const uint32_t target = 16u * (uint32_t)(tcount + 1);
-        long long start = clock64();
-        while ((int)(ld_acquire_gpu(my_cnt) - target) < 0) {
-          if (clock64() - start > 8000000000ll) {
-            printf("llamole_b200: statistics exchange timed out (block %d warp %d)\n", blockIdx.x, warp);
+      // poll this row's four mailboxes (one per column slice) until all carry this tile's tag
+      {
+        float s = 0.f, ss = 0.f;
+        uint32_t pending = 0xFu;
+        const long long start = clock64();
+        while (pending) {
+#pragma unroll
+          for (int src = 0; src < NS; ++src) {
+            if (pending & (1u << src)) {
+              const uint4 v = ld_mailbox(gstats + src * GEMM_BM + rloc);
+              if (v.y == tag && v.w == tag) {
+                s += __uint_as_float(v.x), ss += __uint_as_float(v.z);
+                pending &= ~(1u << src);
+              }
+            }
+          }
+          if (pending && clock64() - start > 8000000000ll) {
+            printf("llamole_b200: statistics exchange timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
             __trap();
           }
         }
-      }
-      __syncwarp();
-      if (tr) GLN_TRACE(tcount, 4, clock64());
-      {
-        float s = 0.f, ss = 0.f;
-#pragma unroll
-        for (int src = 0; src < NS; ++src) {
-          const float2 p = __ldcg(gstats + src * GEMM_BM + rloc);
-          s += p.x, ss += p.y;
-        }
+        if (tr) GLN_TRACE(tcount, 4, clock64());
         const float mean = s * inv_n;
         const float var = fmaxf(ss * inv_n - mean * mean, 0.0f);
         a.rstd = rsqrtf(var + 1e-5f);
@@ -883,8 +889,8 @@ int launch_gemm_ln(const void* A, int lda, const void* W, int ldw, int M, int N,
 
 
 size_t gemm_ln_pair_workspace_bytes() {
-  // counters: one 128-byte line per (group, rank); statistics: [group][2 parities][2 ranks][4 slices][128] float2
-  return (size_t)GLN_PAIR_MAX_GROUPS * 2 * 128 + (size_t)GLN_PAIR_MAX_GROUPS * 2 * 2 * 4 * GEMM_BM * sizeof(float2);
+  // statistics mailboxes: [group][2 tile parities][2 ranks][4 slices][128 rows] x 16 bytes
+  return (size_t)GLN_PAIR_MAX_GROUPS * 2 * 2 * 4 * GEMM_BM * sizeof(uint4);
 }
 
 int launch_gemm_ln_pair(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const GemmLnArgs& e, void* sync_ws,
@@ -922,9 +928,11 @@ int launch_gemm_ln_pair(const void* A, int lda, const void* W, int ldw, int M, i
   }
   const int num_mb = ceil_div(M, 2 * GEMM_BM);
   const int G = num_mb < max_groups ? num_mb : max_groups;
-  uint32_t* cnt = reinterpret_cast<uint32_t*>(sync_ws);
-  float2* stats = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(sync_ws) + (size_t)GLN_PAIR_MAX_GROUPS * 2 * 128);
-  LLB_CUDA_OK(cudaMemsetAsync(cnt, 0, (size_t)GLN_PAIR_MAX_GROUPS * 2 * 128, stream));
+  uint4* stats = reinterpret_cast<uint4*>(sync_ws);
+  // launch-unique tag prefix: stale mailboxes of earlier launches (or whatever the workspace held before) never match
+  static std::atomic<uint32_t> epoch{0x5eed};
+  LLB_CHECK_ARG(ceil_div(num_mb, G) < 4096, "gemm_ln_pair: M=%d is too large for the mailbox tags", M);
+  const uint32_t tag_base = epoch.fetch_add(1) << 12;
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeCooperative;   // every CTA of the grid is resident: the groups spin on each other
@@ -936,7 +944,7 @@ int launch_gemm_ln_pair(const void* A, int lda, const void* W, int ldw, int M, i
     cudaError_t err = cudaErrorNotSupported;
     if (cooperative) {
       cfg.numAttrs = 1;
-      err = cudaLaunchKernelEx(&cfg, gemm_ln_pair_kernel, tmA, tmBh, tmX, tmXb, tmXpf, M, K, G, e, cnt, stats);
+      err = cudaLaunchKernelEx(&cfg, gemm_ln_pair_kernel, tmA, tmBh, tmX, tmXb, tmXpf, M, K, G, e, stats, tag_base);
       if (err != cudaSuccess) {
         (void)cudaGetLastError();
         cooperative = false;   // this driver does not combine clusters with cooperative launch; the grid still fits the device
@@ -944,7 +952,7 @@ int launch_gemm_ln_pair(const void* A, int lda, const void* W, int ldw, int M, i
     }
     if (!cooperative) {
       cfg.numAttrs = 0;
-      err = cudaLaunchKernelEx(&cfg, gemm_ln_pair_kernel, tmA, tmBh, tmX, tmXb, tmXpf, M, K, G, e, cnt, stats);
+      err = cudaLaunchKernelEx(&cfg, gemm_ln_pair_kernel, tmA, tmBh, tmX, tmXb, tmXpf, M, K, G, e, stats, tag_base);
     }
     LLB_CUDA_OK(err);
   }

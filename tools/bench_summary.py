@@ -8,3 +8,8 @@ print("gin graphs/s %.0f  ms %.3f  agg_frac %.3f  mlp_tf %.0f  e2e %.0f" % (g["v
 print("  " + "  ".join("%s=%.3f" % (k, v["ms_per_forward"]) for k, v in g["kernel_breakdown"].items()))
 if d.get("cpu_baseline"): print("cpu", d["cpu_baseline"]["value"], g.get("cpu_baseline", {}).get("value"))
 print("clocks", d["clocks"])
+
+if d.get("predictor"):
+    q = d["predictor"]
+    print("predictor graphs/s %.0f  ms %.2f  head_frac %s  e2e %.0f" % (q["value"], q["ms_per_batch"], q["roofline"]["frac"], q["e2e"]["value"]))
+    print("  " + "  ".join("%s=%.3f" % (k, v["ms_per_batch"]) for k, v in q["kernel_breakdown"].items()))

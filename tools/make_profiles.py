@@ -116,6 +116,7 @@ if os.path.exists(rep):
         if "EpiQKV" in name: slot = "gemm_qkv"
         elif "attention" in name: slot = "attention"
         elif "row_ln" in name: slot = "ln_mod_res"
+        elif "gemm_ln" in name: slot = "gemm_proj" if prev == "attention" else "gemm_fc2"   # fused GEMM + LayerNorm tails
         elif "EpiBiasAct<1" in name: slot = "gemm_fc1"
         elif "EpiBiasAct<0" in name: slot = "gemm_fc2" if prev == "gemm_fc1" else "gemm_proj"
         prev = slot
