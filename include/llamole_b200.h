@@ -263,6 +263,11 @@ int llb_gin_predictor_forward(llb_gin* h, const float* c, float* logits, llb_str
 int llb_gin_predictor_topk(llb_gin* h, const float* c, int k, float* topk_prob, int32_t* topk_idx,
                            llb_stream_t stream);
 int64_t llb_gin_launch_count(const llb_gin* h);
+/* The softmax + top-k stage on its own (graph_predictor/model.py:177-179: F.softmax(logits, dim=1) then torch.topk):
+ * logits (rows, ld) fp32 with W valid columns -> topk_prob / topk_idx (rows, k), value descending, ties to the lowest
+ * index.  One streaming pass per row, plus an exact selection-pass redo of the rows flagged in `scratch` (rows int32). */
+int llb_softmax_topk(const float* logits, int rows, int W, int ld, int k, float* topk_prob, int32_t* topk_idx,
+                     int32_t* scratch, llb_stream_t stream);
 
 /* CostMLP.forward (graph_predictor/model.py:387-391): softplus(W1 relu(W0 fp + b0) + b1).
  * fps (n,2048) fp32, out (n) fp32. */

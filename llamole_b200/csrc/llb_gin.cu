@@ -253,7 +253,8 @@ __global__ void gin_text_operand_kernel(const float* __restrict__ c, const float
 // softmax + top-k of one logits row per CTA (graph_predictor/model.py:177-179).  k selection passes over the
 // L2-resident row; ties resolve to the lowest index like torch.topk's stable behaviour on CPU.
 __global__ void __launch_bounds__(1024) gin_topk_kernel(const float* __restrict__ logits, int ld, int W, int k, float* __restrict__ topv,
-                                                        int32_t* __restrict__ topi) {
+                                                        int32_t* __restrict__ topi, const int32_t* __restrict__ only_flagged) {
+  if (only_flagged != nullptr && only_flagged[blockIdx.x] == 0) return;   // the single-pass kernel already produced this row
   __shared__ float red_v[32];
   __shared__ int red_i[32];
   __shared__ float s_max, s_sum, s_lastv;
@@ -320,6 +321,124 @@ __global__ void __launch_bounds__(1024) gin_topk_kernel(const float* __restrict_
   }
 }
 
+// Single-pass softmax + top-k of one logits row per CTA.  Every thread streams its strided share of the row once
+// (float4 loads), keeping an online (max, sum of exp) pair and its own TK_T best entries in registers; the k winners
+// are then drawn by k block-wide arg-max rounds over the per-thread heads.  A thread whose LAST kept entry gets drawn
+// might have dropped a better one, so it flags the row and gin_topk_kernel (k selection passes, exact for any input)
+// redoes it -- with strided ownership that needs 4 of the top k in one of 1024 residue classes.  Order: value
+// descending, ties to the lowest index, like the selection-pass kernel.
+constexpr int TK_T = 4;
+__device__ __forceinline__ bool tk_before(float v, int i, float w, int j) { return v > w || (v == w && i < j); }
+
+__global__ void __launch_bounds__(1024) gin_topk_stream_kernel(const float* __restrict__ logits, int ld, int W, int k,
+                                                               float* __restrict__ topv, int32_t* __restrict__ topi,
+                                                               int32_t* __restrict__ redo_flag) {
+  __shared__ float red_v[32];
+  __shared__ float red_s[32];
+  __shared__ int red_i[32];
+  __shared__ float s_v;
+  __shared__ int s_i;
+  __shared__ float s_max, s_sum;
+  __shared__ int s_redo;
+  const float* row = logits + (size_t)blockIdx.x * ld;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float bv[TK_T];
+  int bi[TK_T];
+#pragma unroll
+  for (int j = 0; j < TK_T; ++j) bv[j] = -INFINITY, bi[j] = 0x7fffffff;
+  float lm = -INFINITY, ls = 0.f;
+  auto visit = [&](float v, int c) {
+    if (v > lm) {   // online softmax in base 2
+      ls *= exp2f((lm - v) * 1.4426950408889634f);
+      lm = v;
+    }
+    ls += exp2f((v - lm) * 1.4426950408889634f);
+    if (v > bv[TK_T - 1]) {   // strict: among equal values the earlier (lower) index stays
+      bv[TK_T - 1] = v, bi[TK_T - 1] = c;
+#pragma unroll
+      for (int j = TK_T - 1; j > 0; --j) {
+        if (bv[j] > bv[j - 1]) {
+          const float tv = bv[j]; bv[j] = bv[j - 1]; bv[j - 1] = tv;
+          const int ti = bi[j]; bi[j] = bi[j - 1]; bi[j - 1] = ti;
+        }
+      }
+    }
+  };
+  const bool vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0);
+  if (vec) {
+    const int W4 = W >> 2;
+    for (int c4 = tid; c4 < W4; c4 += 1024) {
+      const float4 q = __ldcs(reinterpret_cast<const float4*>(row) + c4);   // streamed once: do not keep it in L2
+      visit(q.x, 4 * c4), visit(q.y, 4 * c4 + 1), visit(q.z, 4 * c4 + 2), visit(q.w, 4 * c4 + 3);
+    }
+    for (int c = (W4 << 2) + tid; c < W; c += 1024) visit(row[c], c);
+  } else {
+    for (int c = tid; c < W; c += 1024) visit(row[c], c);
+  }
+  // block (max, sum)
+  float m = warp_max(lm);
+  if (lane == 0) red_v[warp] = m;
+  if (tid == 0) s_redo = 0;
+  __syncthreads();
+  if (warp == 0) {
+    const float x = warp_max(red_v[lane]);
+    if (lane == 0) s_max = x;
+  }
+  __syncthreads();
+  m = s_max;
+  float s = (lm == -INFINITY) ? 0.f : ls * exp2f((lm - m) * 1.4426950408889634f);
+  s = warp_sum(s);
+  if (lane == 0) red_s[warp] = s;
+  __syncthreads();
+  if (warp == 0) {
+    const float x = warp_sum(red_s[lane]);
+    if (lane == 0) s_sum = x;
+  }
+  __syncthreads();
+  const float inv = 1.0f / s_sum;
+  // k arg-max rounds over the per-thread heads
+  int head = 0;
+  for (int r = 0; r < k; ++r) {
+    float cv = -INFINITY;
+    int ci = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < TK_T; ++j)
+      if (j == head) cv = bv[j], ci = bi[j];
+    float wv = cv;
+    int wi = ci;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, wv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+      if (tk_before(ov, oi, wv, wi)) wv = ov, wi = oi;
+    }
+    if (lane == 0) red_v[warp] = wv, red_i[warp] = wi;
+    __syncthreads();
+    if (warp == 0) {
+      wv = red_v[lane], wi = red_i[lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, wv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+        if (tk_before(ov, oi, wv, wi)) wv = ov, wi = oi;
+      }
+      if (lane == 0) {
+        s_v = wv, s_i = wi;
+        topv[(size_t)blockIdx.x * k + r] = exp2f((wv - m) * 1.4426950408889634f) * inv;
+        topi[(size_t)blockIdx.x * k + r] = wi;
+      }
+    }
+    __syncthreads();
+    if (ci == s_i && ci != 0x7fffffff) {   // my head was drawn (indices are unique)
+      ++head;
+      if (head == TK_T) s_redo = 1;        // my kept list is exhausted: a dropped entry could have been next
+    }
+    // (s_v / s_i are rewritten only after the next __syncthreads pair, every thread has read them by then)
+  }
+  __syncthreads();
+  if (tid == 0) redo_flag[blockIdx.x] = s_redo;
+}
+
 __global__ void cost_mlp_kernel(const float* __restrict__ w0, const float* __restrict__ b0, const float* __restrict__ w1,
                                 const float* __restrict__ b1, const float* __restrict__ fps, int fp_dim, int latent,
                                 float* __restrict__ out) {
@@ -370,6 +489,7 @@ struct llb_gin {
   __nv_bfloat16* hz = nullptr;
   float* head_out = nullptr;
   float* logits_ws = nullptr;
+  int32_t* topk_redo = nullptr;   // per row of a logits chunk: redo with the selection-pass kernel
   int chunk_rows = 0;
   template <class T>
   const T* w(size_t off) const { return reinterpret_cast<const T*>(blob + off); }
@@ -399,7 +519,10 @@ static int gin_carve(llb_gin* g, void* ws, size_t ws_bytes, int n, int e, int B,
   g->hz = a.take<__nv_bfloat16>((size_t)B * G.HH);
   if (!G.predictor) g->head_out = a.take<float>((size_t)B * H);
   g->chunk_rows = B < TOPK_CHUNK ? B : TOPK_CHUNK;
-  if (G.predictor && want_logits) g->logits_ws = a.take<float>((size_t)g->chunk_rows * G.out_dim);
+  if (G.predictor && want_logits) {
+    g->logits_ws = a.take<float>((size_t)g->chunk_rows * G.out_dim);
+    g->topk_redo = a.take<int32_t>(g->chunk_rows);
+  }
   *need = align_up(a.off, 256);
   return LLB_OK;
 }
@@ -705,14 +828,29 @@ int llb_gin_predictor_topk(llb_gin* g, const float* c, int k, float* topk_prob, 
     LLB_TRY(gemm_bias_act(g->hz + (size_t)r0 * G.HH, G.HH, g->w<void>(G.head4_w), G.HH, g->w<float>(G.head4_b), g->logits_ws, G.out_dim,
                           rows, G.out_dim, G.HH, LLB_ACT_NONE, true, s, &g->ctr));
     ProfScope prof(LLB_PROF_GIN_TOPK, s);
-    gin_topk_kernel<<<rows, 1024, 0, s>>>(g->logits_ws, G.out_dim, G.out_dim, k, topk_prob + (size_t)r0 * k, topk_idx + (size_t)r0 * k);
+    gin_topk_stream_kernel<<<rows, 1024, 0, s>>>(g->logits_ws, G.out_dim, G.out_dim, k, topk_prob + (size_t)r0 * k, topk_idx + (size_t)r0 * k,
+                                                 g->topk_redo);
+    gin_topk_kernel<<<rows, 1024, 0, s>>>(g->logits_ws, G.out_dim, G.out_dim, k, topk_prob + (size_t)r0 * k, topk_idx + (size_t)r0 * k,
+                                          g->topk_redo);
     LLB_CUDA_OK(cudaGetLastError());
-    g->launches++;
+    g->launches += 2;
   }
   return LLB_OK;
 }
 
 int64_t llb_gin_launch_count(const llb_gin* g) { return g ? g->launches + g->ctr.launches : 0; }
+
+int llb_softmax_topk(const float* logits, int rows, int W, int ld, int k, float* topk_prob, int32_t* topk_idx, int32_t* scratch,
+                     llb_stream_t stream) {
+  LLB_TRY(require_sm100());
+  LLB_CHECK_ARG(logits && topk_prob && topk_idx && scratch && rows >= 1 && W >= 1 && ld >= W && k >= 1 && k <= W,
+                "llb_softmax_topk: bad argument (rows=%d W=%d ld=%d k=%d)", rows, W, ld, k);
+  cudaStream_t s = (cudaStream_t)stream;
+  gin_topk_stream_kernel<<<rows, 1024, 0, s>>>(logits, ld, W, k, topk_prob, topk_idx, scratch);
+  gin_topk_kernel<<<rows, 1024, 0, s>>>(logits, ld, W, k, topk_prob, topk_idx, scratch);
+  LLB_CUDA_OK(cudaGetLastError());
+  return LLB_OK;
+}
 
 int llb_cost_mlp(const float* w0, const float* b0, const float* w1, const float* b1, const float* fps, int n, int fp_dim,
                  int latent, float* out, llb_stream_t stream) {

@@ -337,3 +337,34 @@ def test_gin_predictor_matches_reference(gin_small):
     assert overlap >= 0.9
     cost = gp.cost_from_fingerprints(fx["fps"])
     assert torch.allclose(cost.cpu(), fx["cost"], atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ softmax + top-k
+@pytest.mark.parametrize("rows,W,k,case", [(7, 64, 10, "random"), (5, 20000, 50, "random"), (3, 180576, 50, "random"),
+                                           (4, 20000, 50, "one_residue"), (4, 5000, 50, "ties"), (2, 4099, 17, "ragged")])
+def test_softmax_topk_matches_torch(rows, W, k, case):
+    """Streaming top-k (and its selection-pass redo) against torch.softmax + a stable sort, bit-exact indices."""
+    g = torch.Generator(device="cpu").manual_seed(rows * 31 + W)
+    ld = W + (4 - W % 4) % 4 if case != "ragged" else W + 3
+    logits = torch.full((rows, ld), float("nan"))
+    vals = torch.randn(rows, W, generator=g) * 0.4
+    if case == "one_residue":      # six of the largest live in the columns one thread owns (float4 c4 = 3 and 3 + 1024): forces the redo path
+        for r in range(rows):
+            vals[r, torch.tensor([12, 13, 14, 15, 4108, 4109])] = 5.0 + torch.rand(6, generator=g)
+    if case == "ties":
+        vals = torch.round(vals * 4) / 4    # heavy ties: order must fall back to the lowest index
+    logits[:, :W] = vals
+    d = logits.to(DEV)
+    prob = torch.empty(rows, k, device=DEV)
+    idx = torch.empty(rows, k, device=DEV, dtype=torch.int32)
+    scratch = torch.empty(rows, device=DEV, dtype=torch.int32)
+    lib = _cabi.lib()
+    _cabi.check(lib.llb_softmax_topk(_cabi.ptr(d), rows, W, ld, k, _cabi.ptr(prob), _cabi.ptr(idx), _cabi.ptr(scratch), _cabi.stream_ptr()),
+                "llb_softmax_topk")
+    torch.cuda.synchronize()
+    p = torch.softmax(vals.double(), dim=1)
+    order = torch.argsort(-vals.double(), dim=1, stable=True)[:, :k]
+    assert torch.equal(idx.cpu().long(), order)
+    assert torch.allclose(prob.cpu().double(), torch.gather(p, 1, order), rtol=2e-5, atol=1e-9)
+    if case == "one_residue":
+        assert int(scratch.sum()) == rows      # every row needed the redo
