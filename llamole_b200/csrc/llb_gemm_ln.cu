@@ -158,7 +158,11 @@ __device__ __forceinline__ void gln_pass2(const GlnPass2& a, const CUtensorMap* 
       const uint32_t xa = a.xstg + rr * 128 + ((sl ^ (rr & 7)) << 4);
       const float4 d = lds128(xa);
       const float4 o = make_float4(res[it].x + d.x, res[it].y + d.y, res[it].z + d.z, res[it].w + d.w);
-      sts128(xa, o);
+      if (GLN_EXP(64)) {
+        if (it * 4 < a.rows_left) *reinterpret_cast<float4*>(const_cast<float*>(xp)) = o;   // experiment: x through generic stores
+      } else {
+        sts128(xa, o);
+      }
       sts64(a.xbstg + rr * 64 + ((((sl >> 1) ^ (rr >> 1)) & 3) << 4) + (sl & 1) * 8, pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
       // next chunk's residual segment: in flight during that chunk's TMEM load and arithmetic
       if (c + 32 < GLN_BN / 2 && it * 4 < a.rows_left && !GLN_EXP(4)) res[it] = *reinterpret_cast<const float4*>(xp + 32);
@@ -167,7 +171,7 @@ __device__ __forceinline__ void gln_pass2(const GlnPass2& a, const CUtensorMap* 
     fence_proxy_async_smem();
     __syncwarp();
     if (elect_one()) {
-      if (!GLN_EXP(1)) tma_store_2d(tmX, reinterpret_cast<const void*>(__cvta_shared_to_generic(a.xstg)), a.gcol + c, a.grow);
+      if (!GLN_EXP(1) && !GLN_EXP(64)) tma_store_2d(tmX, reinterpret_cast<const void*>(__cvta_shared_to_generic(a.xstg)), a.gcol + c, a.grow);
       if (!GLN_EXP(2)) tma_store_2d(tmXb, reinterpret_cast<const void*>(__cvta_shared_to_generic(a.xbstg)), a.gcol + c, a.grow);
       bulk_commit();
     }
@@ -209,7 +213,7 @@ __device__ __forceinline__ void gln_stage_tile(const GemmLnArgs& e, const CUtens
   const int ngroups = cnt + 1;
   if (lane == 0) {
     glist[4] = ngroups;
-    if (m0 < M) l2_prefetch_tile(tmXpf, n0, m0);   // this CTA's 128 x 256 block of the residual stream
+    if (m0 < M && tmXpf != nullptr && !GLN_EXP(32)) l2_prefetch_tile(tmXpf, n0, m0);   // this CTA's 128 x 256 block of the residual stream
   }
   __syncwarp();
   if (ngroups <= GLN_MAX_GROUPS) {
@@ -526,8 +530,12 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 // accumulator stage overlaps with the next tile's MMAs.  All CTAs of the persistent grid must be co-resident (the grid
 // is launched cooperatively, never larger than the device holds).
 // ------------------------------------------------------------------------------------------------------------------
-struct GlnPairSmem {
-  static constexpr int STAGES = 4;
+// STAGES x MODST: (4, 2) for short K (the epilogue is the long pole: the stager must run ahead), (5, 1) for long K (the main
+// loop is: one more 32 KB ring stage rides out the DRAM latency jitter the epilogue's own traffic causes).
+template <int STAGES_, int MODST_>
+struct GlnPairSmemT {
+  static constexpr int STAGES = STAGES_;
+  static constexpr int MODST = MODST_;
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;            // 16 KB: this CTA's 128 rows
   static constexpr int B_BYTES = (GLN_BN / 2) * GEMM_BK * 2;       // 16 KB: this CTA's half of the pair's 256 W rows
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -537,14 +545,15 @@ struct GlnPairSmem {
   static constexpr int OFF_XSTG = STAGES * STAGE_BYTES;
   static constexpr int OFF_XBSTG = OFF_XSTG + GEMM_EPI_WARPS * XSTG_PER_WARP;
   static constexpr int OFF_MOD = OFF_XBSTG + GEMM_EPI_WARPS * XBSTG_PER_WARP;
-  static constexpr int OFF_BIAS = OFF_MOD + 2 * MOD_STAGE_FLOATS * 4;
+  static constexpr int OFF_BIAS = OFF_MOD + MODST * MOD_STAGE_FLOATS * 4;
   static constexpr int OFF_PART = OFF_BIAS + GLN_BN * 4;
   static constexpr int OFF_ROWINFO = OFF_PART + 2 * GEMM_BM * 8;
-  static constexpr int OFF_GLIST = OFF_ROWINFO + 2 * GEMM_BM * 8;
+  static constexpr int OFF_GLIST = OFF_ROWINFO + MODST * GEMM_BM * 8;
   static constexpr int OFF_BARS = OFF_GLIST + 64;
   static constexpr int TOTAL = OFF_BARS + 256 + 1024;
 };
-static_assert(GlnPairSmem::TOTAL <= 232448, "gemm_ln pair kernel shared memory exceeds the 227 KB per-CTA limit");
+static_assert(GlnPairSmemT<4, 2>::TOTAL <= 232448 && GlnPairSmemT<5, 1>::TOTAL <= 232448,
+              "gemm_ln pair kernel shared memory exceeds the 227 KB per-CTA limit");
 
 // Statistics mailbox entry: {sum, tag, sum of squares, tag}.  Data and flag travel in the same 8-byte halves (each
 // half is an atomic access), so the exchange needs no fence, no atomic and no counter: a reader simply re-reads until both
@@ -559,13 +568,15 @@ __device__ __forceinline__ uint4 ld_mailbox(const uint4* p) {
   return v;
 }
 
+template <int STAGES_, int MODST_>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
                     const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXb,
                     const __grid_constant__ CUtensorMap tmXpf, int M, int K, int G, GemmLnArgs e, uint4* sync_stats,
-                    uint32_t tag_base) {
-  using S = GlnPairSmem;
+                    uint32_t tag_base, int prefetch_x) {
+  using S = GlnPairSmemT<STAGES_, MODST_>;
   constexpr int STAGES = S::STAGES;
+  constexpr int MODST = S::MODST;
   constexpr int BN = GLN_BN;
   constexpr int NS = 4;   // column slices of 256 = pairs per group
   const uint32_t rank = cluster_rank();
@@ -610,6 +621,8 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], 2 * GEMM_EPI_WARPS);
+    }
+    for (int a = 0; a < MODST; ++a) {
       mbar_init(&mod_full[a], 1);
       mbar_init(&mod_empty[a], GEMM_EPI_WARPS);
     }
@@ -697,9 +710,10 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int mb = grp; mb < num_mb; mb += G) {
       const int m0 = mb * 2 * GEMM_BM + (int)rank * GEMM_BM;
       mbar_wait(&mod_empty[st], ph ^ 1);
-      gln_stage_tile(e, &tmXpf, modS + (size_t)st * S::MOD_STAGE_FLOATS, rowinfoS + st * GEMM_BM, glistS + st * 8, m0, n0, M, lane);
+      gln_stage_tile(e, prefetch_x ? &tmXpf : nullptr, modS + (size_t)st * S::MOD_STAGE_FLOATS, rowinfoS + st * GEMM_BM, glistS + st * 8, m0, n0, M,
+                     lane);
       if (lane == 0) mbar_arrive(&mod_full[st]);
-      if (++st == 2) {
+      if (++st == MODST) {
         st = 0;
         ph ^= 1;
       }
@@ -719,14 +733,16 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     a.gcol = n0 + cbase;
     int acc = 0;
     uint32_t acc_phase = 0;
+    int ms = 0;           // modulation stage / phase (MODST stages)
+    uint32_t mph = 0;
     int tcount = 0;
     const bool tr = warp == 0 && lane == 0;
     for (int mb = grp; mb < num_mb; mb += G, ++tcount) {
       const int m0 = mb * 2 * GEMM_BM + (int)rank * GEMM_BM;
       if (tr) GLN_TRACE(tcount, 0, clock64());
-      mbar_wait(&mod_full[acc], acc_phase);
-      const int2 info = rowinfoS[acc * GEMM_BM + rloc];
-      const bool staged = glistS[acc * 8 + 4] <= GLN_MAX_GROUPS;
+      mbar_wait(&mod_full[ms], mph);
+      const int2 info = rowinfoS[ms * GEMM_BM + rloc];
+      const bool staged = glistS[ms * 8 + 4] <= GLN_MAX_GROUPS;
       if (tr) GLN_TRACE(tcount, 1, clock64());
       mbar_wait(&tmem_full[acc], acc_phase);
       if (tr) GLN_TRACE(tcount, 2, clock64());
@@ -737,11 +753,15 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         __syncwarp();
         if (lane == 0) {
           mbar_arrive_cluster(&tmem_empty[acc], 0);
-          mbar_arrive(&mod_empty[acc]);
+          mbar_arrive(&mod_empty[ms]);
         }
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
+        }
+        if (++ms == MODST) {
+          ms = 0;
+          mph ^= 1;
         }
         continue;
       }
@@ -794,7 +814,7 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       a.trace_tile = tr ? tcount : -1;
       if (GLN_EXP(8)) {
       } else if (staged) {
-        a.mod_s = smem_u32(modS + (size_t)acc * S::MOD_STAGE_FLOATS + (size_t)info.x * 2 * BN + cbase);
+        a.mod_s = smem_u32(modS + (size_t)ms * S::MOD_STAGE_FLOATS + (size_t)info.x * 2 * BN + cbase);
         gln_pass2<true>(a, &tmX, &tmXb, res, lane);
       } else {
         const size_t off = (size_t)info.y * e.mod_ld + n0 + cbase;
@@ -806,11 +826,15 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       __syncwarp();
       if (lane == 0) {
         mbar_arrive_cluster(&tmem_empty[acc], 0);
-        mbar_arrive(&mod_empty[acc]);
+        mbar_arrive(&mod_empty[ms]);
       }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
+      }
+      if (++ms == MODST) {
+        ms = 0;
+        mph ^= 1;
       }
     }
     if (lane == 0) bulk_wait_all();
@@ -913,19 +937,26 @@ int launch_gemm_ln_pair(const void* A, int lda, const void* W, int ldw, int M, i
   LLB_TRY(make_tensor_map_2d(&tmX, e.x, 4, M, N, e.ldx, 32, 32, 128));
   LLB_TRY(make_tensor_map_2d(&tmXb, e.xb, 2, M, N, e.ldxb, 32, 32, 64));
   LLB_TRY(make_tensor_map_2d(&tmXpf, e.x, 4, M, N, e.ldx, GLN_BN, GEMM_BM, 0));
-  static bool configured = false;
-  static int max_groups = 0;
+  // long K: the main loop is the long pole -> 5-stage ring, single modulation stage, no L2 prefetch of the residual (its
+  // 128 KB TMA prefetch per tile delays the ring's loads; the residual reads hide behind the MMAs anyway);
+  // short K: the epilogue is -> modulation stager two tiles ahead, residual prefetched.
+  const bool long_k = K > 2048;
+  auto kern = long_k ? gemm_ln_pair_kernel<5, 1> : gemm_ln_pair_kernel<4, 2>;
+  const int smem_bytes = long_k ? GlnPairSmemT<5, 1>::TOTAL : GlnPairSmemT<4, 2>::TOTAL;
+  static bool configured[2] = {false, false};
+  static int max_groups_v[2] = {0, 0};
   static bool cooperative = true;
-  if (!configured) {
-    LLB_CUDA_OK(cudaFuncSetAttribute(gemm_ln_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GlnPairSmem::TOTAL));
+  if (!configured[long_k]) {
+    LLB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     cudaLaunchConfig_t q = {};
-    q.blockDim = dim3(GEMM_THREADS), q.dynamicSmemBytes = GlnPairSmem::TOTAL, q.gridDim = dim3(2 * (num_sms() / 2));
+    q.blockDim = dim3(GEMM_THREADS), q.dynamicSmemBytes = smem_bytes, q.gridDim = dim3(2 * (num_sms() / 2));
     int n = 0;
-    LLB_CUDA_OK(cudaOccupancyMaxActiveClusters(&n, gemm_ln_pair_kernel, &q));
-    max_groups = n / 4 < GLN_PAIR_MAX_GROUPS ? n / 4 : GLN_PAIR_MAX_GROUPS;
-    LLB_CHECK_ARG(max_groups > 0, "gemm_ln_pair: fewer than four CTA pairs fit on this device");
-    configured = true;
+    LLB_CUDA_OK(cudaOccupancyMaxActiveClusters(&n, kern, &q));
+    max_groups_v[long_k] = n / 4 < GLN_PAIR_MAX_GROUPS ? n / 4 : GLN_PAIR_MAX_GROUPS;
+    LLB_CHECK_ARG(max_groups_v[long_k] > 0, "gemm_ln_pair: fewer than four CTA pairs fit on this device");
+    configured[long_k] = true;
   }
+  const int max_groups = max_groups_v[long_k];
   const int num_mb = ceil_div(M, 2 * GEMM_BM);
   const int G = num_mb < max_groups ? num_mb : max_groups;
   uint4* stats = reinterpret_cast<uint4*>(sync_ws);
@@ -933,18 +964,19 @@ int launch_gemm_ln_pair(const void* A, int lda, const void* W, int ldw, int M, i
   static std::atomic<uint32_t> epoch{0x5eed};
   LLB_CHECK_ARG(ceil_div(num_mb, G) < 4096, "gemm_ln_pair: M=%d is too large for the mailbox tags", M);
   const uint32_t tag_base = epoch.fetch_add(1) << 12;
+  const int prefetch_x = long_k ? 0 : 1;
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeCooperative;   // every CTA of the grid is resident: the groups spin on each other
   attr[0].val.cooperative = 1;
-  cfg.blockDim = dim3(GEMM_THREADS), cfg.dynamicSmemBytes = GlnPairSmem::TOTAL, cfg.stream = stream, cfg.attrs = attr;
+  cfg.blockDim = dim3(GEMM_THREADS), cfg.dynamicSmemBytes = smem_bytes, cfg.stream = stream, cfg.attrs = attr;
   cfg.gridDim = dim3(2 * 4 * G);
   {
     ProfScope prof(ctr ? ctr->slot : LLB_PROF_GEMM_OTHER, stream);
     cudaError_t err = cudaErrorNotSupported;
     if (cooperative) {
       cfg.numAttrs = 1;
-      err = cudaLaunchKernelEx(&cfg, gemm_ln_pair_kernel, tmA, tmBh, tmX, tmXb, tmXpf, M, K, G, e, stats, tag_base);
+      err = cudaLaunchKernelEx(&cfg, kern, tmA, tmBh, tmX, tmXb, tmXpf, M, K, G, e, stats, tag_base, prefetch_x);
       if (err != cudaSuccess) {
         (void)cudaGetLastError();
         cooperative = false;   // this driver does not combine clusters with cooperative launch; the grid still fits the device
@@ -952,7 +984,7 @@ int launch_gemm_ln_pair(const void* A, int lda, const void* W, int ldw, int M, i
     }
     if (!cooperative) {
       cfg.numAttrs = 0;
-      err = cudaLaunchKernelEx(&cfg, gemm_ln_pair_kernel, tmA, tmBh, tmX, tmXb, tmXpf, M, K, G, e, stats, tag_base);
+      err = cudaLaunchKernelEx(&cfg, kern, tmA, tmBh, tmX, tmXb, tmXpf, M, K, G, e, stats, tag_base, prefetch_x);
     }
     LLB_CUDA_OK(err);
   }
