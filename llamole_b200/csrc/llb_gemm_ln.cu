@@ -190,6 +190,110 @@ __device__ __forceinline__ void gln_pass2(const GlnPass2& a, const CUtensorMap* 
 #endif
 }
 
+// Pass 2 with the residual travelling through TMA in BOTH directions (CTA-pair kernel): the residual box of a chunk is
+// TMA-loaded into the warp's swizzled staging tile, each thread (= TMEM lane = row) adds its 32 normalised, modulated
+// values to its own row IN PLACE and packs the bf16 copy, and the same tile is TMA-stored back.  No transposition, no
+// generic global access (generic loads from 8 warps crawl once shared memory has taken the whole L1), 20 instead of 40
+// shared-memory instructions per chunk.  With NXB = 2 staging tiles the next chunk's load is issued a chunk ahead;
+// with NXB = 1 (long K, where the epilogue has slack) load and store of consecutive chunks serialise.
+template <bool STAGED, int NXB>
+__device__ __forceinline__ void gln_pass2_tma(const GlnPass2& a, const CUtensorMap* tmX, const CUtensorMap* tmXb, uint64_t* res_full,
+                                              uint32_t& res_phase, int lane) {
+  float v[32];
+#ifdef LLB_GEMM_TRACE
+  long long tt0 = 0, tt1 = 0, tt2 = 0, tt3 = 0;
+#endif
+#pragma unroll 1
+  for (int ci = 0; ci < GLN_BN / 2 / 32; ++ci) {
+    const int c = ci * 32;
+    const int b = NXB == 2 ? (ci & 1) : 0;
+#ifdef LLB_GEMM_TRACE
+    const long long k0 = clock64();
+#endif
+    tmem_ld32(a.t_row + c, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      const float4 bb = lds128(a.bias_s + (c + 4 * p) * 4);
+      float4 s1, sh;
+      if (STAGED) {
+        s1 = lds128(a.mod_s + (c + 4 * p) * 4);
+        sh = lds128(a.mod_s + (GLN_BN + c + 4 * p) * 4);
+      } else {
+        const float4 gt = __ldg(reinterpret_cast<const float4*>(a.g_gate + c + 4 * p));
+        s1 = __ldg(reinterpret_cast<const float4*>(a.g_scale + c + 4 * p));
+        sh = __ldg(reinterpret_cast<const float4*>(a.g_shift + c + 4 * p));
+        s1.x = (1.0f + s1.x) * gt.x, s1.y = (1.0f + s1.y) * gt.y, s1.z = (1.0f + s1.z) * gt.z, s1.w = (1.0f + s1.w) * gt.w;
+        sh.x *= gt.x, sh.y *= gt.y, sh.z *= gt.z, sh.w *= gt.w;
+      }
+      v[4 * p] = fmaf(fmaf(v[4 * p] + bb.x, a.rstd, a.nmr), s1.x, sh.x);
+      v[4 * p + 1] = fmaf(fmaf(v[4 * p + 1] + bb.y, a.rstd, a.nmr), s1.y, sh.y);
+      v[4 * p + 2] = fmaf(fmaf(v[4 * p + 2] + bb.z, a.rstd, a.nmr), s1.z, sh.z);
+      v[4 * p + 3] = fmaf(fmaf(v[4 * p + 3] + bb.w, a.rstd, a.nmr), s1.w, sh.w);
+    }
+#ifdef LLB_GEMM_TRACE
+    const long long k1 = clock64();
+#endif
+    // the previous chunk's stores have read their staging tiles: the bf16 tile and the other fp32 tile are free
+    if (elect_one()) {
+      bulk_wait_read<0>();
+      if (NXB == 2 && ci + 1 < GLN_BN / 2 / 32) {
+        mbar_arrive_expect_tx(&res_full[b ^ 1], 4096);
+        tma_load_2d(reinterpret_cast<void*>(__cvta_shared_to_generic(a.xstg + (b ^ 1) * 4096)), tmX, &res_full[b ^ 1], a.gcol + c + 32, a.grow);
+      }
+    }
+    __syncwarp();
+#ifdef LLB_GEMM_TRACE
+    const long long k2 = clock64();
+#endif
+    mbar_wait(&res_full[b], (res_phase >> b) & 1u);
+    res_phase ^= 1u << b;
+#ifdef LLB_GEMM_TRACE
+    const long long k3 = clock64();
+#endif
+    const uint32_t xs = a.xstg + b * 4096 + lane * 128;
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      const uint32_t addr = xs + ((p ^ (lane & 7)) << 4);
+      const float4 r = lds128(addr);
+      v[4 * p] += r.x, v[4 * p + 1] += r.y, v[4 * p + 2] += r.z, v[4 * p + 3] += r.w;
+      sts128(addr, make_float4(v[4 * p], v[4 * p + 1], v[4 * p + 2], v[4 * p + 3]));
+    }
+    const uint32_t xbs = a.xbstg + lane * 64;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float4 q;
+      q.x = __uint_as_float(pack_bf16x2(v[8 * j], v[8 * j + 1])), q.y = __uint_as_float(pack_bf16x2(v[8 * j + 2], v[8 * j + 3]));
+      q.z = __uint_as_float(pack_bf16x2(v[8 * j + 4], v[8 * j + 5])), q.w = __uint_as_float(pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+      sts128(xbs + ((j ^ ((lane >> 1) & 3)) << 4), q);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (elect_one()) {
+      if (!GLN_EXP(1)) tma_store_2d(tmX, reinterpret_cast<const void*>(__cvta_shared_to_generic(a.xstg + b * 4096)), a.gcol + c, a.grow);
+      if (!GLN_EXP(2)) tma_store_2d(tmXb, reinterpret_cast<const void*>(__cvta_shared_to_generic(a.xbstg)), a.gcol + c, a.grow);
+      bulk_commit();
+      if (NXB == 1 && ci + 1 < GLN_BN / 2 / 32) {   // single tile: reload it as soon as the store has read it
+        bulk_wait_read<0>();
+        mbar_arrive_expect_tx(&res_full[0], 4096);
+        tma_load_2d(reinterpret_cast<void*>(__cvta_shared_to_generic(a.xstg)), tmX, &res_full[0], a.gcol + c + 32, a.grow);
+      }
+    }
+#ifdef LLB_GEMM_TRACE
+    const long long k4 = clock64();
+    tt0 += k1 - k0, tt1 += k2 - k1, tt2 += k3 - k2, tt3 += k4 - k3;
+#endif
+  }
+#ifdef LLB_GEMM_TRACE
+  if (a.trace_tile >= 0) {
+    GLN_TRACE(a.trace_tile, 11, tt0);   // tmem + math
+    GLN_TRACE(a.trace_tile, 12, tt1);   // wait for the previous stores' smem reads
+    GLN_TRACE(a.trace_tile, 13, tt2);   // wait for the residual load
+    GLN_TRACE(a.trace_tile, 14, tt3);   // add, pack, fence, store issue
+  }
+#endif
+}
+
 // Modulation stager, one warp, one tile: which modulation rows do the tile's 128 token rows use (runs of equal
 // row_group), stage gate*(1+scale) and gate*shift of those rows (this CTA's 256 columns) in shared memory, and pull the
 // CTA's block of the residual stream into L2 for the epilogue's pass 2.
@@ -530,16 +634,18 @@ gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 // accumulator stage overlaps with the next tile's MMAs.  All CTAs of the persistent grid must be co-resident (the grid
 // is launched cooperatively, never larger than the device holds).
 // ------------------------------------------------------------------------------------------------------------------
-// STAGES x MODST: (4, 2) for short K (the epilogue is the long pole: the stager must run ahead), (5, 1) for long K (the main
-// loop is: one more 32 KB ring stage rides out the DRAM latency jitter the epilogue's own traffic causes).
-template <int STAGES_, int MODST_>
+// (STAGES, MODST, NXB): (4, 1, 2) for short K -- the epilogue is the long pole, so every warp gets two fp32 staging tiles and
+// loads the next chunk's residual a chunk ahead; (5, 1, 1) for long K -- the main loop is, and one more 32 KB ring stage
+// rides out the DRAM latency jitter the epilogue's own traffic causes.
+template <int STAGES_, int MODST_, int NXB_>
 struct GlnPairSmemT {
   static constexpr int STAGES = STAGES_;
   static constexpr int MODST = MODST_;
+  static constexpr int NXB = NXB_;   // fp32 staging tiles per epilogue warp
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;            // 16 KB: this CTA's 128 rows
   static constexpr int B_BYTES = (GLN_BN / 2) * GEMM_BK * 2;       // 16 KB: this CTA's half of the pair's 256 W rows
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int XSTG_PER_WARP = 32 * 32 * 4;
+  static constexpr int XSTG_PER_WARP = NXB * 32 * 32 * 4;
   static constexpr int XBSTG_PER_WARP = 32 * 32 * 2;
   static constexpr int MOD_STAGE_FLOATS = GLN_MAX_GROUPS * 2 * GLN_BN;
   static constexpr int OFF_XSTG = STAGES * STAGE_BYTES;
@@ -550,9 +656,9 @@ struct GlnPairSmemT {
   static constexpr int OFF_ROWINFO = OFF_PART + 2 * GEMM_BM * 8;
   static constexpr int OFF_GLIST = OFF_ROWINFO + MODST * GEMM_BM * 8;
   static constexpr int OFF_BARS = OFF_GLIST + 64;
-  static constexpr int TOTAL = OFF_BARS + 256 + 1024;
+  static constexpr int TOTAL = OFF_BARS + 512 + 1024;
 };
-static_assert(GlnPairSmemT<4, 2>::TOTAL <= 232448 && GlnPairSmemT<5, 1>::TOTAL <= 232448,
+static_assert(GlnPairSmemT<4, 1, 2>::TOTAL <= 232448 && GlnPairSmemT<5, 1, 1>::TOTAL <= 232448,
               "gemm_ln pair kernel shared memory exceeds the 227 KB per-CTA limit");
 
 // Statistics mailbox entry: {sum, tag, sum of squares, tag}.  Data and flag travel in the same 8-byte halves (each
@@ -568,15 +674,16 @@ __device__ __forceinline__ uint4 ld_mailbox(const uint4* p) {
   return v;
 }
 
-template <int STAGES_, int MODST_>
+template <int STAGES_, int MODST_, int NXB_>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
                     const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXb,
                     const __grid_constant__ CUtensorMap tmXpf, int M, int K, int G, GemmLnArgs e, uint4* sync_stats,
                     uint32_t tag_base, int prefetch_x) {
-  using S = GlnPairSmemT<STAGES_, MODST_>;
+  using S = GlnPairSmemT<STAGES_, MODST_, NXB_>;
   constexpr int STAGES = S::STAGES;
   constexpr int MODST = S::MODST;
+  constexpr int NXB = S::NXB;
   constexpr int BN = GLN_BN;
   constexpr int NS = 4;   // column slices of 256 = pairs per group
   const uint32_t rank = cluster_rank();
@@ -601,6 +708,7 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* mod_full = bars + 2 * STAGES + 4;
   uint64_t* mod_empty = bars + 2 * STAGES + 6;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 8);
+  uint64_t* res_full = bars + 2 * STAGES + 10;   // [epilogue warp][2]: residual chunk landed in the warp's staging tile
 
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
@@ -626,6 +734,7 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_init(&mod_full[a], 1);
       mbar_init(&mod_empty[a], GEMM_EPI_WARPS);
     }
+    for (int a = 0; a < 2 * GEMM_EPI_WARPS; ++a) mbar_init(&res_full[a], 1);
     fence_mbar_init();
   }
   if (threadIdx.x < BN) biasS[threadIdx.x] = e.bias ? e.bias[n0 + threadIdx.x] : 0.0f;
@@ -735,20 +844,29 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t acc_phase = 0;
     int ms = 0;           // modulation stage / phase (MODST stages)
     uint32_t mph = 0;
+    uint32_t res_phase = 0;   // bit b: phase of this warp's res_full[b]
     int tcount = 0;
     const bool tr = warp == 0 && lane == 0;
     for (int mb = grp; mb < num_mb; mb += G, ++tcount) {
       const int m0 = mb * 2 * GEMM_BM + (int)rank * GEMM_BM;
       if (tr) GLN_TRACE(tcount, 0, clock64());
-      mbar_wait(&mod_full[ms], mph);
-      const int2 info = rowinfoS[ms * GEMM_BM + rloc];
-      const bool staged = glistS[ms * 8 + 4] <= GLN_MAX_GROUPS;
+      // the tile's first residual chunk starts its way into the staging tile now (the previous tile's stores have read it)
+      a.grow = m0 + q * 32;
+      if (elect_one()) {
+        bulk_wait_read<0>();
+        mbar_arrive_expect_tx(&res_full[warp * 2], 4096);
+        tma_load_2d(reinterpret_cast<void*>(__cvta_shared_to_generic(a.xstg)), &tmX, &res_full[warp * 2], a.gcol, a.grow);
+      }
+      __syncwarp();
       if (tr) GLN_TRACE(tcount, 1, clock64());
       mbar_wait(&tmem_full[acc], acc_phase);
       if (tr) GLN_TRACE(tcount, 2, clock64());
       tc_fence_after();
       a.t_row = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16) + cbase;
       if (GLN_EXP(16)) {   // knock-out: empty epilogue (main loop alone)
+        mbar_wait(&res_full[warp * 2], res_phase & 1u);
+        res_phase ^= 1u;
+        mbar_wait(&mod_full[ms], mph);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
@@ -775,15 +893,6 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         st_mailbox(gstats + slice * GEMM_BM + rloc, p0.x + p1.x, p0.y + p1.y, tag);
       }
       if (tr) GLN_TRACE(tcount, 3, clock64());
-      // first residual chunk: in flight while the statistics travel
-      const int row0 = m0 + q * 32 + rsub;
-      a.rows_left = M - row0;
-      a.grow = m0 + q * 32;
-      a.xrow = e.x + (size_t)row0 * e.ldx + n0 + cbase + sl * 4;
-      float4 res[8];
-#pragma unroll
-      for (int it = 0; it < 8; ++it)
-        res[it] = (it * 4 < a.rows_left) ? *reinterpret_cast<const float4*>(a.xrow + it * a.xstride) : make_float4(0.f, 0.f, 0.f, 0.f);
       // poll this row's four mailboxes (one per column slice) until all carry this tile's tag
       {
         float s = 0.f, ss = 0.f;
@@ -812,14 +921,20 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         a.nmr = -mean * a.rstd;
       }
       a.trace_tile = tr ? tcount : -1;
+      // the tile's modulation rows are staged (the stager had pass 1 and the exchange to do it)
+      mbar_wait(&mod_full[ms], mph);
+      const int2 info = rowinfoS[ms * GEMM_BM + rloc];
+      const bool staged = glistS[ms * 8 + 4] <= GLN_MAX_GROUPS;
       if (GLN_EXP(8)) {
+        mbar_wait(&res_full[warp * 2], res_phase & 1u);
+        res_phase ^= 1u;
       } else if (staged) {
         a.mod_s = smem_u32(modS + (size_t)ms * S::MOD_STAGE_FLOATS + (size_t)info.x * 2 * BN + cbase);
-        gln_pass2<true>(a, &tmX, &tmXb, res, lane);
+        gln_pass2_tma<true, NXB>(a, &tmX, &tmXb, &res_full[warp * 2], res_phase, lane);
       } else {
         const size_t off = (size_t)info.y * e.mod_ld + n0 + cbase;
         a.g_shift = e.shift + off, a.g_scale = e.scale + off, a.g_gate = e.gate + off;
-        gln_pass2<false>(a, &tmX, &tmXb, res, lane);
+        gln_pass2_tma<false, NXB>(a, &tmX, &tmXb, &res_full[warp * 2], res_phase, lane);
       }
       if (tr) GLN_TRACE(tcount, 5, clock64());
       tc_fence_before();
@@ -941,8 +1056,8 @@ int launch_gemm_ln_pair(const void* A, int lda, const void* W, int ldw, int M, i
   // 128 KB TMA prefetch per tile delays the ring's loads; the residual reads hide behind the MMAs anyway);
   // short K: the epilogue is -> modulation stager two tiles ahead, residual prefetched.
   const bool long_k = K > 2048;
-  auto kern = long_k ? gemm_ln_pair_kernel<5, 1> : gemm_ln_pair_kernel<4, 2>;
-  const int smem_bytes = long_k ? GlnPairSmemT<5, 1>::TOTAL : GlnPairSmemT<4, 2>::TOTAL;
+  auto kern = long_k ? gemm_ln_pair_kernel<5, 1, 1> : gemm_ln_pair_kernel<4, 1, 2>;
+  const int smem_bytes = long_k ? GlnPairSmemT<5, 1, 1>::TOTAL : GlnPairSmemT<4, 1, 2>::TOTAL;
   static bool configured[2] = {false, false};
   static int max_groups_v[2] = {0, 0};
   static bool cooperative = true;

@@ -22,7 +22,7 @@ int main() {
   cudaMalloc(&trace, 64 * 16 * 8);
   void* ws; const size_t wsb = gemm_ln_pair_workspace_bytes(); cudaMalloc(&ws, wsb);
   const int nexp = 3;
-  const int exps[nexp] = {0, 3, 16, 0, 0, 0};
+  const int exps[nexp] = {0, 3, 16};
   for (int pairmode = 1; pairmode < 2; ++pairmode)
   for (int xi = 0; xi < nexp; ++xi)
   for (int K : {1024, 4096}) {
@@ -50,8 +50,8 @@ int main() {
     std::vector<long long> h(64 * 16);
     cudaMemcpy(h.data(), trace, h.size() * 8, cudaMemcpyDeviceToHost);
     auto T = [&](int t, int s) { return h[(size_t)t * 16 + s]; };
-    printf("tile | epi: phaseA  wait_tmem  pass1  stats_wait  pass2  period | mma: wait_empty  span | pass2: tmem  math+sts  res_wait  coalesced\n");
-    for (int t = 6; t < 8; ++t)
+    printf("tile | epi: phaseA  wait_tmem  pass1  stats_wait  pass2  period | mma: wait_empty  span | pass2: tmem+math  store_read_wait  res_wait  add+store\n");
+    for (int t = 5; t < 9; ++t)
       printf("%3d | %6lld %6lld %6lld %6lld %6lld %6lld | %6lld %6lld | %6lld %6lld %6lld %6lld\n", t, T(t, 1) - T(t, 0), T(t, 2) - T(t, 1), T(t, 3) - T(t, 2),
              T(t, 4) - T(t, 3), T(t, 5) - T(t, 4), T(t, 0) - T(t - 1, 0), T(t, 9) - T(t, 8), T(t, 10) - T(t, 9), T(t, 11), T(t, 12), T(t, 13), T(t, 14));
   }
