@@ -833,12 +833,10 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int rloc = q * 32 + lane;
     const int cbase = ch * (BN / 2);
     const float inv_n = 1.0f / (float)(NS * BN);
-    const int sl = lane & 7, rsub = lane >> 3;
     GlnPass2 a;
     a.xstg = smem_u32(smem + S::OFF_XSTG + warp * S::XSTG_PER_WARP);
     a.xbstg = smem_u32(smem + S::OFF_XBSTG + warp * S::XBSTG_PER_WARP);
     a.bias_s = smem_u32(biasS + cbase);
-    a.xstride = (size_t)4 * e.ldx;
     a.gcol = n0 + cbase;
     int acc = 0;
     uint32_t acc_phase = 0;

@@ -52,7 +52,8 @@ def test_gemm_matches_torch(M, N, K, act, out_f32):
 
 # ------------------------------------------------------------------------------------------------ fused GEMM + LN tail
 @pytest.mark.parametrize("M,N,K,group_len", [(1, 256, 64, 50), (300, 1024, 1024, 50), (1000, 1024, 4096, 50), (777, 512, 256, 7),
-                                             (4097, 1024, 1024, 50), (260, 768, 768, 3), (128 * 41 + 5, 1024, 512, 50), (256 * 40 + 130, 1024, 1024, 50)])
+                                             (4097, 1024, 1024, 50), (260, 768, 768, 3), (128 * 41 + 5, 1024, 512, 50), (256 * 40 + 130, 1024, 1024, 50),
+                                             (600, 1024, 256, 5), (2500, 1024, 4096, 13)])
 @pytest.mark.parametrize("variant", ["cluster", "pair"])
 def test_gemm_ln_residual_matches_torch(M, N, K, group_len, variant):
     """x += gate * (LN(A W^T + b) (1 + scale) + shift) against fp32 torch; rows map to modulation rows in runs of
