@@ -120,8 +120,38 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
+// Descriptor cache: a sampling step re-issues the same ~130 GEMMs on the same buffers every step, and
+// cuTensorMapEncodeTiled costs 1-2 us a call (three to five calls per GEMM) -- at small batch that was most of the step.
+// Direct-mapped, per host thread, keyed on everything that defines the map.
+namespace {
+struct TmapKey {
+  const void* ptr;
+  int elem_bytes, rows, cols, ld, box_cols, box_rows, swizzle;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && elem_bytes == o.elem_bytes && rows == o.rows && cols == o.cols && ld == o.ld && box_cols == o.box_cols &&
+           box_rows == o.box_rows && swizzle == o.swizzle;
+  }
+};
+struct TmapSlot {
+  TmapKey key{};
+  bool valid = false;
+  CUtensorMap map;
+};
+constexpr int TMAP_CACHE_SLOTS = 2048;
+}  // namespace
+
 int make_tensor_map_2d(CUtensorMap* out, const void* ptr, int elem_bytes, int rows, int cols, int ld_elems, int box_cols,
                        int box_rows, int swizzle_bytes) {
+  static thread_local std::vector<TmapSlot> cache(TMAP_CACHE_SLOTS);
+  const TmapKey key{ptr, elem_bytes, rows, cols, ld_elems, box_cols, box_rows, swizzle_bytes};
+  uint64_t hsh = reinterpret_cast<uintptr_t>(ptr) * 0x9E3779B97F4A7C15ull;
+  hsh ^= ((uint64_t)(uint32_t)rows << 32 | (uint32_t)cols) * 0xC2B2AE3D27D4EB4Full;
+  hsh ^= ((uint64_t)(uint32_t)ld_elems << 24 | (uint32_t)box_cols << 12 | (uint32_t)box_rows << 4 | (uint32_t)(elem_bytes ^ swizzle_bytes)) * 0x165667B19E3779F9ull;
+  TmapSlot& slot = cache[(hsh >> 40) % TMAP_CACHE_SLOTS];
+  if (slot.valid && slot.key == key) {
+    *out = slot.map;
+    return LLB_OK;
+  }
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(LLB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -136,6 +166,7 @@ int make_tensor_map_2d(CUtensorMap* out, const void* ptr, int elem_bytes, int ro
   if (r != CUDA_SUCCESS)
     return fail(LLB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for rows=%d cols=%d ld=%d elem=%d box=%dx%d ptr=%p", (int)r, rows,
                 cols, ld_elems, elem_bytes, box_cols, box_rows, ptr);
+  slot.key = key, slot.map = *out, slot.valid = true;
   return LLB_OK;
 }
 
