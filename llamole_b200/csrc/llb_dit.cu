@@ -308,12 +308,15 @@ static int dit_forward(llb_dit* h, int t, cudaStream_t s) {
   const size_t ln_sync_bytes = gemm_ln_pair_workspace_bytes();
   for (int l = 0; l < D; ++l) {
     const float* mod = h->mod + (size_t)l * (B + 1) * 6 * H;
+    // Block 0 sees the SAME token embedding in the conditional and the unconditional half and attention has no
+    // conditioning, so its qkv GEMM and attention run once on Mtok rows; the halves part ways at the first modulation.
+    const bool share0 = l == 0 && h->passes == 2 && fused_ln;
     ctr->slot = LLB_PROF_GEMM_QKV;
     EpiQKV eq{h->qkv, 3 * H, H, h->w<float>(L.qn_w[l]), h->w<float>(L.qn_b[l]), h->w<float>(L.kn_w[l]), h->w<float>(L.kn_b[l]), q_scale};
-    LLB_TRY((launch_gemm<256>(h->xb, H, h->w<void>(L.qkv_w[l]), H, M, 3 * H, H, eq, s, ctr)));
+    LLB_TRY((launch_gemm<256>(h->xb, H, h->w<void>(L.qkv_w[l]), H, share0 ? Mtok : M, 3 * H, H, eq, s, ctr)));
     {
       ProfScope prof(LLB_PROF_ATTENTION, s);
-      dit_attention_kernel<<<dim3(h->passes * B, L.heads), 128, 0, s>>>(h->qkv, h->attn, h->mol_off, B, Mtok, H);
+      dit_attention_kernel<<<dim3((share0 ? 1 : h->passes) * B, L.heads), 128, 0, s>>>(h->qkv, h->attn, h->mol_off, B, Mtok, H);
     }
     LLB_CUDA_OK(cudaGetLastError());
     h->launches++;
@@ -326,8 +329,14 @@ static int dit_forward(llb_dit* h, int t, cudaStream_t s) {
     ctr->slot = LLB_PROF_GEMM_PROJ;
     if (fused_ln) {
       f.bias = h->w<float>(L.proj_b[l]), f.shift = mod, f.scale = mod + H, f.gate = mod + 2 * H;
-      if (fused_pair) LLB_TRY(launch_gemm_ln_pair(h->attn, H, h->w<void>(L.proj_w[l]), H, M, H, H, f, h->ln_sync, ln_sync_bytes, s, ctr));
-      else LLB_TRY(launch_gemm_ln(h->attn, H, h->w<void>(L.proj_w[l]), H, M, H, H, f, s, ctr));
+      // with the shared block-0 attention both halves project the same Mtok attention rows onto their own residual rows
+      for (int part = 0; part < (share0 ? 2 : 1); ++part) {
+        GemmLnArgs fp = f;
+        const int rows = share0 ? Mtok : M;
+        fp.row_group = f.row_group + (size_t)part * Mtok, fp.x = f.x + (size_t)part * Mtok * H, fp.xb = f.xb + (size_t)part * Mtok * H;
+        if (fused_pair) LLB_TRY(launch_gemm_ln_pair(h->attn, H, h->w<void>(L.proj_w[l]), H, rows, H, H, fp, h->ln_sync, ln_sync_bytes, s, ctr));
+        else LLB_TRY(launch_gemm_ln(h->attn, H, h->w<void>(L.proj_w[l]), H, rows, H, H, fp, s, ctr));
+      }
     } else {
       LLB_TRY(gemm_bias_act(h->attn, H, h->w<void>(L.proj_w[l]), H, h->w<float>(L.proj_b[l]), h->y, H, M, H, H, LLB_ACT_NONE, false, s, ctr));
       a.shift = mod, a.scale = mod + H, a.gate = mod + 2 * H;
