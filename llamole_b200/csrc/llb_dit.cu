@@ -316,7 +316,7 @@ static int dit_forward(llb_dit* h, int t, cudaStream_t s) {
     LLB_TRY((launch_gemm<256>(h->xb, H, h->w<void>(L.qkv_w[l]), H, share0 ? Mtok : M, 3 * H, H, eq, s, ctr)));
     {
       ProfScope prof(LLB_PROF_ATTENTION, s);
-      dit_attention_kernel<<<dim3((share0 ? 1 : h->passes) * B, L.heads), 128, 0, s>>>(h->qkv, h->attn, h->mol_off, B, Mtok, H);
+      dit_attention_kernel<<<(unsigned)((share0 ? 1 : h->passes) * B * L.heads), 128, 0, s>>>(h->qkv, h->attn, h->mol_off, B, Mtok, H, L.heads);
     }
     LLB_CUDA_OK(cudaGetLastError());
     h->launches++;

@@ -112,12 +112,14 @@ __device__ __forceinline__ void mma_bf16_16816(float* c, uint32_t a0, uint32_t a
 }
 
 __global__ void __launch_bounds__(128) dit_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
-                                                            const int32_t* __restrict__ mol_off, int B, int Mtok, int H) {
+                                                            const int32_t* __restrict__ mol_off, int B, int Mtok, int H, int heads) {
   __shared__ __align__(16) __nv_bfloat16 sQ[64 * ATT_LD];
   __shared__ __align__(16) __nv_bfloat16 sK[64 * ATT_LD];
   __shared__ __align__(16) __nv_bfloat16 sV[64 * ATT_LD];
-  const int seq = blockIdx.x;  // pass * B + molecule
-  const int head = blockIdx.y;
+  // heads vary fastest across the grid: the 16 CTAs that read the q/k/v head slices of one sequence's rows (6 KB
+  // contiguous per token) run together, which keeps the DRAM pages they share open
+  const int head = blockIdx.x % heads;
+  const int seq = blockIdx.x / heads;  // pass * B + molecule
   const int b = seq % B, pass = seq / B;
   const int row0 = pass * Mtok + mol_off[b];
   const int n = mol_off[b + 1] - mol_off[b];
