@@ -396,7 +396,14 @@ __global__ void __launch_bounds__(1024) gin_topk_stream_kernel(const float* __re
   }
   __syncthreads();
   const float inv = 1.0f / s_sum;
-  // k arg-max rounds over the per-thread heads
+  // k arg-max rounds over the per-thread heads.  A candidate is one sortable 64-bit key (order-preserving float bits in
+  // the high word, inverted index in the low word: larger key = larger value, ties to the lower index), so a warp
+  // arg-max is two REDUX instructions and every warp reduces the 32 warp winners itself: one barrier per round.
+  __shared__ uint32_t key_hi[2][32], key_lo[2][32];
+  auto enc_hi = [](float v) {
+    const uint32_t u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  };
   int head = 0;
   for (int r = 0; r < k; ++r) {
     float cv = -INFINITY;
@@ -404,36 +411,26 @@ __global__ void __launch_bounds__(1024) gin_topk_stream_kernel(const float* __re
 #pragma unroll
     for (int j = 0; j < TK_T; ++j)
       if (j == head) cv = bv[j], ci = bi[j];
-    float wv = cv;
-    int wi = ci;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, wv, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
-      if (tk_before(ov, oi, wv, wi)) wv = ov, wi = oi;
-    }
-    if (lane == 0) red_v[warp] = wv, red_i[warp] = wi;
+    const uint32_t hi = enc_hi(cv), lo = 0xffffffffu - (uint32_t)ci;   // exhausted / empty slots: (-inf, index 2^31-1), loses to any real entry
+    const uint32_t whi = __reduce_max_sync(0xffffffffu, hi);
+    const uint32_t wlo = __reduce_max_sync(0xffffffffu, hi == whi ? lo : 0u);
+    const int buf = r & 1;
+    if (lane == 0) key_hi[buf][warp] = whi, key_lo[buf][warp] = wlo;
     __syncthreads();
-    if (warp == 0) {
-      wv = red_v[lane], wi = red_i[lane];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, wv, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
-        if (tk_before(ov, oi, wv, wi)) wv = ov, wi = oi;
-      }
-      if (lane == 0) {
-        s_v = wv, s_i = wi;
-        topv[(size_t)blockIdx.x * k + r] = exp2f((wv - m) * 1.4426950408889634f) * inv;
-        topi[(size_t)blockIdx.x * k + r] = wi;
-      }
+    const uint32_t ghi = __reduce_max_sync(0xffffffffu, key_hi[buf][lane]);
+    const uint32_t glo = __reduce_max_sync(0xffffffffu, key_hi[buf][lane] == ghi ? key_lo[buf][lane] : 0u);
+    const int wi = (int)(0xffffffffu - glo);
+    if (tid == 0) {
+      const uint32_t ub = (ghi & 0x80000000u) ? (ghi & 0x7fffffffu) : ~ghi;
+      const float wv = __uint_as_float(ub);
+      topv[(size_t)blockIdx.x * k + r] = exp2f((wv - m) * 1.4426950408889634f) * inv;
+      topi[(size_t)blockIdx.x * k + r] = wi;
     }
-    __syncthreads();
-    if (ci == s_i && ci != 0x7fffffff) {   // my head was drawn (indices are unique)
+    if (ci == wi && ci != 0x7fffffff) {   // my head was drawn (indices are unique)
       ++head;
       if (head == TK_T) s_redo = 1;        // my kept list is exhausted: a dropped entry could have been next
     }
-    // (s_v / s_i are rewritten only after the next __syncthreads pair, every thread has read them by then)
+    // the other key buffer is rewritten next round; everybody has read this one before the barrier after that
   }
   __syncthreads();
   if (tid == 0) redo_flag[blockIdx.x] = s_redo;
