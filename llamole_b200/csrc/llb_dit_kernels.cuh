@@ -243,6 +243,358 @@ __global__ void __launch_bounds__(128) dit_attention_kernel(const __nv_bfloat16*
 }
 
 // ------------------------------------------------------------------------------------------------
+// The same attention with the operands delivered by TMA (LLB_ATTN=3).  The kernel above spends a third of its
+// shared-memory wavefronts on getting q/k/v INTO shared memory (12 LDG.128 + 12 STS.128 per thread, through registers);
+// here one thread issues three 64 x 64 box loads of the qkv matrix (128-byte swizzle, so ldmatrix stays conflict-free
+// without padding) and the CTA waits on one mbarrier.  Rows past the end of the sequence hold the next sequence's
+// tokens (or zeros past the end of the matrix): keys >= n are masked to -inf exactly as before, so they contribute
+// p = 0 times a finite value; queries >= n are never stored.
+// ------------------------------------------------------------------------------------------------
+constexpr int ATTT_TILE = 64 * DIT_DH * 2;   // one 64-row operand tile (8 KB)
+
+__device__ __forceinline__ uint32_t attt_swz(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
+
+__global__ void __launch_bounds__(128) dit_attention_tma_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ out,
+                                                                const int32_t* __restrict__ mol_off, int B, int Mtok, int H, int heads) {
+  __shared__ __align__(1024) uint8_t tiles[3 * ATTT_TILE];
+  __shared__ __align__(8) uint64_t bar;
+  const int head = blockIdx.x % heads;
+  const int seq = blockIdx.x / heads;  // pass * B + molecule
+  const int b = seq % B, pass = seq / B;
+  const int row0 = pass * Mtok + mol_off[b];
+  const int n = mol_off[b + 1] - mol_off[b];
+  if (n == 0) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_arrive_expect_tx(&bar, 3 * ATTT_TILE);
+#pragma unroll
+    for (int mat = 0; mat < 3; ++mat) tma_load_2d(tiles + mat * ATTT_TILE, &tmQKV, &bar, mat * H + head * DIT_DH, row0);
+  }
+  if (warp * 16 >= n) return;
+  const uint32_t sQ = smem_u32(tiles), sK = sQ + ATTT_TILE, sV = sK + ATTT_TILE;
+  const int npad = (n + 15) & ~15;
+  const int ntiles = npad >> 3;  // key tiles of 8
+  mbar_wait(&bar, 0);
+  // ---- S = Q K^T
+  float s[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    uint32_t a0, a1, a2, a3;
+    ldsm_x4(sQ + attt_swz(warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, ks * 2 + (lane >> 4)), a0, a1, a2, a3);
+#pragma unroll
+    for (int jp = 0; jp < 4; ++jp) {
+      if (jp * 2 < ntiles) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4(sK + attt_swz(jp * 16 + (lane & 7) + (lane >> 4) * 8, ks * 2 + ((lane >> 3) & 1)), b0, b1, b2, b3);
+        mma_bf16_16816(s[2 * jp], a0, a1, a2, a3, b0, b1);
+        mma_bf16_16816(s[2 * jp + 1], a0, a1, a2, a3, b2, b3);
+      }
+    }
+  }
+  // ---- softmax over keys < n (rows g and g+8 of this warp's 16)
+  const int t4 = lane & 3;
+  float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int key = j * 8 + t4 * 2 + e;
+      if (key >= n) s[j][e] = s[j][2 + e] = -INFINITY;
+      m0 = fmaxf(m0, s[j][e]);
+      m1 = fmaxf(m1, s[j][2 + e]);
+    }
+  }
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+  float l0 = 0.f, l1 = 0.f;
+  uint32_t p[8][2];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float e0 = exp2f(s[j][0] - m0), e1 = exp2f(s[j][1] - m0);
+    const float e2 = exp2f(s[j][2] - m1), e3 = exp2f(s[j][3] - m1);
+    l0 += e0 + e1;
+    l1 += e2 + e3;
+    p[j][0] = pack_bf16x2(e0, e1);
+    p[j][1] = pack_bf16x2(e2, e3);
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  // ---- O = P V
+  float o[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    if (ks * 16 < npad) {
+      const uint32_t a0 = p[2 * ks][0], a1 = p[2 * ks][1], a2 = p[2 * ks + 1][0], a3 = p[2 * ks + 1][1];
+#pragma unroll
+      for (int dp = 0; dp < 4; ++dp) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4_t(sV + attt_swz(ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, dp * 2 + (lane >> 4)), b0, b1, b2, b3);
+        mma_bf16_16816(o[2 * dp], a0, a1, a2, a3, b0, b1);
+        mma_bf16_16816(o[2 * dp + 1], a0, a1, a2, a3, b2, b3);
+      }
+    }
+  }
+  const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+  const int g = lane >> 2;
+  // stage the warp's 16 x 64 output tile in its own (already consumed) Q rows (same swizzle), then write 16-byte
+  // pieces so that 8 lanes cover one 128-byte row segment
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(sQ + attt_swz(warp * 16 + g, j) + t4 * 4), "r"(pack_bf16x2(o[j][0] * inv0, o[j][1] * inv0)) : "memory");
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(sQ + attt_swz(warp * 16 + g + 8, j) + t4 * 4), "r"(pack_bf16x2(o[j][2] * inv1, o[j][3] * inv1))
+                 : "memory");
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int pp = lane + 32 * i;
+    const int r = pp >> 3, ch = pp & 7;
+    const int grow = warp * 16 + r;
+    uint4 v4;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v4.x), "=r"(v4.y), "=r"(v4.z), "=r"(v4.w) : "r"(sQ + attt_swz(grow, ch)));
+    if (grow < n) *reinterpret_cast<uint4*>(out + (size_t)(row0 + grow) * H + head * DIT_DH + ch * 8) = v4;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Attention on tcgen05 (default when the head count is even).  The mma.sync kernel above is bound by the shared-memory
+// pipe: every warp re-reads K and V with ldmatrix and the loads themselves go global -> registers -> shared.  Here the
+// tensor core reads its operands straight from the tiles TMA wrote:
+//   unit      = (sequence, pair of heads).  Q2 / K2 / V2 are 128-row tiles: rows 0..63 head h0, rows 64..127 head h1
+//               (six 64 x 64 TMA boxes of the qkv matrix, 128-byte swizzle; rows past the sequence end belong to the
+//               next sequence or are zero-filled, and are masked).
+//   S         = Q2 . K2^T  (M128 x N128 x K64, fp32 in TMEM): the two diagonal 64 x 64 blocks are the two heads' scores.
+//   softmax   = thread r owns row r: tcgen05.ld of its block's 64 columns, exp2 (q carries dh^-0.5 log2 e), masked keys
+//               contribute exactly 0, bf16 row -> the block-diagonal P tile (K-major, swizzled; the off-diagonal
+//               blocks stay zero from the start).
+//   O         = P . V2 (M128 x N64 x K128): V2 is consumed as an MN-major operand, i.e. exactly the [key][dh] tile TMA
+//               delivered, no transposition.  O / row-sum -> bf16 -> coalesced masked stores.
+// Persistent CTA, 6 warps: 0..3 softmax + epilogue (thread = TMEM lane = row), 4 TMA producer (3-stage ring), 5 MMA issuer.
+// ------------------------------------------------------------------------------------------------
+constexpr int ATTU_STAGES = 3;
+constexpr int ATTU_TILE = 128 * 64 * 2;                       // one 128-row operand tile (16 KB)
+constexpr int ATTU_STAGE_BYTES = 3 * ATTU_TILE;               // Q2 | K2 | V2
+constexpr int ATTU_OFF_P = ATTU_STAGES * ATTU_STAGE_BYTES;    // per softmax group: two K-halves of [128 rows][64 keys] bf16
+constexpr int ATTU_OFF_BARS = ATTU_OFF_P + 2 * 2 * ATTU_TILE;
+constexpr int ATTU_SMEM = ATTU_OFF_BARS + 256 + 1024;
+constexpr int ATTU_THREADS = 320;                             // 2 softmax groups x 4 warps, TMA producer, MMA issuer
+
+__global__ void __launch_bounds__(ATTU_THREADS, 1)
+dit_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ out, const int32_t* __restrict__ mol_off,
+                          int B, int Mtok, int H, int heads, int num_units, int dbg) {
+  extern __shared__ uint8_t attu_raw[];
+  uint8_t* smem = attu_raw + ((1024u - (smem_u32(attu_raw) & 1023u)) & 1023u);
+  uint8_t* smP = smem + ATTU_OFF_P;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATTU_OFF_BARS);
+  uint64_t* full = bars;                      // [STAGES] TMA -> MMA
+  uint64_t* empty = bars + ATTU_STAGES;       // [STAGES] MMA (P V done) -> TMA
+  uint64_t* s_full = bars + 2 * ATTU_STAGES;  // [2] S of the group's unit is in TMEM
+  uint64_t* p_full = s_full + 2;              // [2] P is in shared memory (and S consumed)
+  uint64_t* o_full = s_full + 4;              // [2] O is in TMEM
+  uint64_t* o_empty = s_full + 6;             // [2] O consumed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 8);
+  const int warp = uniform_warp_idx();
+  const int lane = threadIdx.x & 31;
+  const int hpairs = heads >> 1;
+
+  if (warp == 8 && elect_one()) {
+    tma_prefetch_desc(&tmQKV);
+    for (int i = 0; i < ATTU_STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&s_full[g], 1);
+      mbar_init(&p_full[g], 4);
+      mbar_init(&o_full[g], 1);
+      mbar_init(&o_empty[g], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 9) tmem_alloc(tmem_slot, 512);
+  // the off-diagonal blocks of P are never written: zero both groups' tiles once
+  for (int i = threadIdx.x; i < 4 * ATTU_TILE / 16; i += ATTU_THREADS) reinterpret_cast<uint4*>(smP)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    // ---------------- TMA producer ----------------
+    int st = 0;
+    uint32_t ph = 0;
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+      const int seq = u / hpairs, hp = u % hpairs;
+      const int b = seq % B, pass = seq / B;
+      const int n = mol_off[b + 1] - mol_off[b];
+      if (n == 0) continue;
+      const int row0 = pass * Mtok + mol_off[b];
+      mbar_wait(&empty[st], ph ^ 1);
+      if (elect_one()) {
+        uint8_t* base = smem + st * ATTU_STAGE_BYTES;
+        mbar_arrive_expect_tx(&full[st], ATTU_STAGE_BYTES);
+#pragma unroll
+        for (int mat = 0; mat < 3; ++mat)
+#pragma unroll
+          for (int hl = 0; hl < 2; ++hl)
+            tma_load_2d(base + mat * ATTU_TILE + hl * (ATTU_TILE / 2), &tmQKV, &full[st], mat * H + (2 * hp + hl) * DIT_DH, row0);
+      }
+      __syncwarp();
+      if (++st == ATTU_STAGES) {
+        st = 0;
+        ph ^= 1;
+      }
+    }
+  } else if (warp == 9) {
+    // ---------------- MMA issuer: S of unit k, then P V of unit k - 1 (the other group's softmax runs in between) ----------------
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64) | (1u << 16);   // B (= V2) is MN-major
+    const uint64_t p_desc0 = umma_desc_k128(smem_u32(smP));
+    auto issue_pv = [&](int g, uint32_t gph, int st) {
+      mbar_wait(&p_full[g], gph);
+      mbar_wait(&o_empty[g], gph ^ 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t p_desc = p_desc0 + (uint64_t)(g * 2 * (ATTU_TILE >> 4));
+        const uint64_t v_desc = umma_desc_k128(smem_u32(smem + st * ATTU_STAGE_BYTES + 2 * ATTU_TILE));
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)   // 16 keys per step: P K-half kk / 4, 32 bytes along its rows; V2 16 rows = 2 KB further down
+          umma_bf16(tmem_base + g * 256 + 128, p_desc + (uint64_t)((kk >> 2) * (ATTU_TILE >> 4) + (kk & 3) * 2), v_desc + (uint64_t)(kk * 128), idesc_o,
+                    kk != 0 ? 1u : 0u);
+        umma_commit(&o_full[g]);
+        umma_commit(&empty[st]);
+      }
+      __syncwarp();
+    };
+    int k = 0, st = 0, prev_st = 0;
+    uint32_t ph = 0;
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+      const int seq = u / hpairs;
+      const int b = seq % B;
+      if (mol_off[b + 1] - mol_off[b] == 0) continue;
+      const int g = k & 1;
+      const uint64_t q_desc = umma_desc_k128(smem_u32(smem + st * ATTU_STAGE_BYTES));
+      const uint64_t k_desc = q_desc + (ATTU_TILE >> 4);
+      mbar_wait(&full[st], ph);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int kq = 0; kq < 4; ++kq) umma_bf16(tmem_base + g * 256, q_desc + 2 * kq, k_desc + 2 * kq, idesc_s, kq != 0 ? 1u : 0u);
+        umma_commit(&s_full[g]);
+      }
+      __syncwarp();
+      if (k > 0) issue_pv(g ^ 1, (uint32_t)(((k - 1) >> 1) & 1), prev_st);
+      prev_st = st;
+      ++k;
+      if (++st == ATTU_STAGES) {
+        st = 0;
+        ph ^= 1;
+      }
+    }
+    if (k > 0) issue_pv((k - 1) & 1, (uint32_t)(((k - 1) >> 1) & 1), prev_st);
+  } else {
+    // ---------------- softmax + epilogue: group = warp / 4, thread = row of the stacked 128-row tile ----------------
+    const int grp = warp >> 2, wq = warp & 3;
+    const int r = wq * 32 + lane;            // TMEM lane
+    const int hl = r >> 6;                   // head of the pair
+    const uint32_t t_s = tmem_base + ((uint32_t)(wq * 32) << 16) + grp * 256 + hl * 64;
+    const uint32_t t_o = tmem_base + ((uint32_t)(wq * 32) << 16) + grp * 256 + 128;
+    const uint32_t pbase = smem_u32(smP) + grp * 2 * ATTU_TILE;
+    const uint32_t prow = pbase + hl * ATTU_TILE + r * 128;   // this row's 128 bytes inside its diagonal block
+    int k = 0;
+    uint32_t up = 0;
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+      const int seq = u / hpairs, hp = u % hpairs;
+      const int b = seq % B, pass = seq / B;
+      const int n = mol_off[b + 1] - mol_off[b];
+      if (n == 0) continue;
+      if (((k++) & 1) != grp) continue;      // the other group's unit
+      const int row0 = pass * Mtok + mol_off[b];
+      mbar_wait(&s_full[grp], up);
+      tc_fence_after();
+      float sc[64];
+      tmem_ld32(t_s, sc);
+      tmem_ld32(t_s + 32, sc + 32);
+      tmem_ld_wait();
+      float m = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 64; ++j) m = fmaxf(m, j < n ? sc[j] : -INFINITY);
+      float l = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float e[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          e[i] = (c * 8 + i < n) ? ((dbg & 2) ? 1.0f : exp2f(sc[c * 8 + i] - m)) : 0.f;
+          l += e[i];
+        }
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + ((c ^ (r & 7)) << 4)), "r"(pack_bf16x2(e[0], e[1])),
+                     "r"(pack_bf16x2(e[2], e[3])), "r"(pack_bf16x2(e[4], e[5])), "r"(pack_bf16x2(e[6], e[7]))
+                     : "memory");
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[grp]);
+      const float inv = 1.0f / l;
+      mbar_wait(&o_full[grp], up);
+      tc_fence_after();
+      tmem_ld32(t_o, sc);
+      tmem_ld32(t_o + 32, sc + 32);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_empty[grp]);
+      if (dbg & 4) { up ^= 1; continue; }
+      // stage the normalised bf16 row in this row's (now idle) P slot, then 8 lanes write one 128-byte row segment
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + ((c ^ (r & 7)) << 4)),
+                     "r"(pack_bf16x2(sc[c * 8] * inv, sc[c * 8 + 1] * inv)), "r"(pack_bf16x2(sc[c * 8 + 2] * inv, sc[c * 8 + 3] * inv)),
+                     "r"(pack_bf16x2(sc[c * 8 + 4] * inv, sc[c * 8 + 5] * inv)), "r"(pack_bf16x2(sc[c * 8 + 6] * inv, sc[c * 8 + 7] * inv))
+                     : "memory");
+      __syncwarp();
+      const int whl = (wq * 32) >> 6;                               // the warp's 32 rows all belong to one head
+      const uint32_t wbase = pbase + whl * ATTU_TILE + (wq * 32) * 128;
+      __nv_bfloat16* obase = out + (size_t)row0 * H + (2 * hp + whl) * DIT_DH;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int pp = lane + 32 * i;
+        const int rr = pp >> 3, ch = pp & 7;
+        const int q_idx = ((wq * 32) & 63) + rr;
+        uint4 v4;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v4.x), "=r"(v4.y), "=r"(v4.z), "=r"(v4.w)
+                     : "r"(wbase + rr * 128 + ((ch ^ ((wq * 32 + rr) & 7)) << 4)));
+        if (q_idx < n && !(dbg & 1)) *reinterpret_cast<uint4*>(obase + (size_t)q_idx * H + ch * 8) = v4;
+      }
+      __syncwarp();   // the staged rows are read before the group's next unit overwrites them with P
+      up ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Fused per-molecule step kernel.
 // ------------------------------------------------------------------------------------------------
 struct DitTablesDev {
