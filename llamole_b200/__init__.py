@@ -7,5 +7,6 @@ are drop-ins for the reference classes of the same names under src/model/graph_{
 from .graph_decoder import GraphDiT, set_smiles_backend  # noqa: F401
 from .graph_encoder import GraphCLIP  # noqa: F401
 from .graph_predictor import GraphPredictor  # noqa: F401
+from .condition_queue import ConditionQueue  # noqa: F401
 
 __version__ = "0.1.0"

@@ -65,18 +65,60 @@ def all_gather_rows(t: torch.Tensor, group=None) -> torch.Tensor:
     return torch.cat([o[:s] for o, s in zip(outs, sizes)], dim=0)
 
 
+def pack_graphs(X: torch.Tensor, E: torch.Tensor, n: torch.Tensor) -> torch.Tensor:
+    """Compact wire format of sampled graphs: per molecule one row of
+    `2 + N + N(N+1)/2` bytes = node count (little-endian u16) | atom classes + 1 | upper triangle (with diagonal) of
+    the bond classes + 1, so the masked value -1 travels as 0.  1327 B per molecule at N=50 instead of 20.4 KB of int64.
+    E must be symmetric (the sampler mirrors the upper triangle, diffusion_utils.py:316-349)."""
+    B, N = X.shape
+    if E.shape != (B, N, N) or n.shape != (B,):
+        raise ValueError(f"pack_graphs: X {tuple(X.shape)}, E {tuple(E.shape)}, n {tuple(n.shape)}")
+    if not torch.equal(E, E.transpose(1, 2)):
+        raise ValueError("pack_graphs: E is not symmetric")
+    iu = torch.triu_indices(N, N, device=E.device)
+    lo, hi = int(min(X.min(), E.min())) if B else 0, int(max(X.max(), E.max())) if B else 0
+    if lo < -1 or hi > 254:
+        raise ValueError("pack_graphs: classes must lie in [-1, 254]")
+    nn_ = n.to(torch.int64)
+    head = torch.stack([nn_ & 0xFF, nn_ >> 8], dim=1)
+    row = torch.cat([head, X.to(torch.int64) + 1, E[:, iu[0], iu[1]].to(torch.int64) + 1], dim=1)
+    return row.to(torch.uint8)
+
+
+def unpack_graphs(wire: torch.Tensor, N: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Inverse of pack_graphs: (X (B,N), E (B,N,N), n (B,)) int64."""
+    B = wire.shape[0]
+    if wire.shape[1] != 2 + N + N * (N + 1) // 2:
+        raise ValueError(f"unpack_graphs: row of {wire.shape[1]} bytes does not match N={N}")
+    w = wire.to(torch.int64)
+    n = w[:, 0] | (w[:, 1] << 8)
+    X = w[:, 2:2 + N] - 1
+    iu = torch.triu_indices(N, N, device=wire.device)
+    E = torch.empty((B, N, N), dtype=torch.int64, device=wire.device)
+    tri = w[:, 2 + N:] - 1
+    E[:, iu[0], iu[1]] = tri
+    E[:, iu[1], iu[0]] = tri
+    return X, E, n
+
+
 def sample_graphs_sharded(generate_fn: Callable, properties: torch.Tensor, text_embedding: torch.Tensor, n_nodes: torch.Tensor,
-                          seed: int = 0, group=None, **kw):
+                          seed: int = 0, group=None, wire: str = "compact", **kw):
     """Shard a sampling batch over the ranks and gather the integer graphs.
 
     generate_fn(properties, text_embedding, n_nodes=..., seed=..., mol_index_base=...) -> (X, E, n) as
-    GraphDiT.generate_graphs.  Every rank passes the FULL batch and receives the FULL result.
+    GraphDiT.generate_graphs.  Every rank passes the FULL batch and receives the FULL result.  The one exchange is an
+    all-gather of the compact byte rows of pack_graphs (`wire="full"` gathers the int64 tensors instead).
     """
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     s, e = shard_range(properties.shape[0], rank, world)
     X, E, n = generate_fn(properties[s:e], text_embedding[s:e], n_nodes=n_nodes[s:e], seed=seed, mol_index_base=s, **kw)
-    return all_gather_rows(X, group), all_gather_rows(E, group), all_gather_rows(n, group)
+    if world == 1:
+        return X, E, n
+    if wire == "full":
+        return all_gather_rows(X, group), all_gather_rows(E, group), all_gather_rows(n, group)
+    Xg, Eg, ng = unpack_graphs(all_gather_rows(pack_graphs(X, E, n), group), X.shape[1])
+    return Xg.to(X.dtype), Eg.to(E.dtype), ng.to(n.dtype)
 
 
 def encode_graphs_sharded(forward_fn: Callable, x, edge_index, edge_attr, batch, num_graphs: Optional[int] = None, group=None,
