@@ -303,7 +303,13 @@ static int dit_forward(llb_dit* h, int t, cudaStream_t s) {
                         B + 1, 2 * L.d0, H, LLB_ACT_NONE, true, s, ctr));
   // 3. transformer blocks
   const float q_scale = 1.4426950408889634f / sqrtf((float)DIT_DH);
-  const bool fused_ln = gemm_ln_supported(H, H) && gemm_ln_supported(H, F) && gemm_ln_enabled();
+  // Latency regime (a handful of molecules, e.g. the reference's per-prompt batches of 6): below ~2000 token rows the
+  // fused block tails occupy only 2 M / 256 row groups of 8 SMs each and stream their weights through too few TMA rings
+  // (fc2 + LN 33 us vs 19 + 9 us for GEMM<64> + row kernel at 406 rows), so the unfused pair is used unless
+  // LLB_FUSED_LN says otherwise.  Measured cross-over: 978 rows 2.54 vs 3.06 ms/step, 3870 rows 4.45 vs 4.20.
+  static const bool ln_env_set = getenv("LLB_FUSED_LN") != nullptr;
+  const bool latency_regime = !ln_env_set && M < 2048;
+  const bool fused_ln = gemm_ln_supported(H, H) && gemm_ln_supported(H, F) && gemm_ln_enabled() && !latency_regime;
   // LLB_FUSED_LN: 0 = GEMM + row kernel; 1 = fused, 4-CTA cluster kernel (projection only: with K = 4 H its single-CTA
   // main loop loses more than the row kernel costs); 2 = cluster kernel for both halves; 3 (default) = fused on the
   // CTA-pair main loop for both halves when H = 1024, else as 1.
