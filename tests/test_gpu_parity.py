@@ -461,3 +461,141 @@ def test_dit_parity_with_fused_block_tails_forced():
                         "denoiser_logits or full_size or teacher_forced or end_to_end"], env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert " passed" in r.stdout and "failed" not in r.stdout
+
+
+# ------------------------------------------------------------------------------------------------ edge cases vs the oracle
+def _graph_batch(sizes, seed, edges=True):
+    """Concatenate synthetic molecule-like graphs of the given node counts (0 = an empty graph in the middle of the batch)."""
+    xs, eis, eas, bs = [], [], [], []
+    base = 0
+    for gi, n in enumerate(sizes):
+        if n == 0:
+            continue
+        x, ei, ea, _ = synth.molecular_graphs(1, seed=seed + gi, min_nodes=n, max_nodes=n)
+        xs.append(x)
+        bs.append(torch.full((n,), gi, dtype=torch.int64))
+        if edges:
+            eis.append(ei + base)
+            eas.append(ea)
+        base += n
+    ei = torch.cat(eis, 1) if eis else torch.zeros((2, 0), dtype=torch.int64)
+    ea = torch.cat(eas) if eas else torch.zeros((0,), dtype=torch.int64)
+    return torch.cat(xs), ei, ea, torch.cat(bs)
+
+
+@pytest.mark.parametrize("case,sizes,edges", [
+    ("single_graph", [17], True),
+    ("single_atom_graphs", [1, 1, 1, 1, 1], True),
+    ("no_edges_at_all", [3, 1, 8, 2], False),
+    ("ragged_with_large", [1, 50, 2, 200, 9, 64, 65, 1], True),
+    ("many_tiny", [2] * 300 + [1] * 45, True),
+])
+def test_gin_edge_cases_vs_oracle(case, sizes, edges):
+    """Degenerate and ragged graph batches (the reference has no tests; these are the shapes its
+    callers produce: single molecules from one_step_reaction, single atoms, edge-less fragments, large reactants) against
+    the CPU oracle with the same weights.  H=256, L=3: stated tolerance max |d| <= 3e-3 sqrt(768/H) on unit-norm rows."""
+    from oracle import llamole_oracle as O
+
+    L, H = 3, 256
+    enc, proj = synth.gin_encoder_state_dicts(L, H, seed=21)
+    g = GraphCLIP(L, H, 0.0, {})
+    g.molecule_encoder.load_state_dict(enc)
+    g.molecule_projection.load_state_dict(proj)
+    g = g.to(DEV)
+    x, ei, ea, b = _graph_batch(sizes, seed=len(sizes) * 7 + 1, edges=edges)
+    with torch.no_grad():
+        ref = O.gin_encoder_forward(enc, proj, L, x, ei, ea, b)
+    out = g(x.to(DEV), ei.to(DEV), ea.to(DEV), b.to(DEV))
+    torch.cuda.synchronize()
+    assert out.shape == ref.shape and bool(torch.isfinite(out).all())
+    mx, rms = _stats(out.cpu(), ref)
+    print(f"\n[parity] GIN {case}: {len(sizes)} graphs, {x.numel()} nodes, {ea.numel()} edges: max|d|={mx:.2e} rms={rms:.2e}")
+    assert mx <= 3e-3 * math.sqrt(768 / H), (case, mx)
+
+
+def test_gin_predictor_edge_cases_vs_oracle():
+    """Predictor trunk + head on a ragged batch with single-atom and large graphs, with and without the text condition."""
+    from oracle import llamole_oracle as O
+
+    L, H, D = 2, 256, 777
+    sd = synth.gin_predictor_state_dict(L, H, D, seed=5)
+    d = tempfile.mkdtemp()
+    synth.write_predictor_checkpoint(d, L, H, D, 5, with_cost=False)
+    gp = GraphPredictor(L, H, 0.0, D, {}, {i: f"T{i}" for i in range(D)})
+    gp.init_model(d)
+    gp = gp.to(DEV)
+    x, ei, ea, b = _graph_batch([1, 33, 2, 130, 1, 7], seed=3)
+    c = torch.nn.functional.silu(torch.randn(6, 768, generator=torch.Generator().manual_seed(1)))
+    for cond in (c, None):
+        with torch.no_grad():
+            ref = O.gin_predictor_forward(sd, L, x, ei, ea, b, cond)
+        got = gp(x.to(DEV), ei.to(DEV), ea.to(DEV), b.to(DEV), None if cond is None else cond.to(DEV))
+        torch.cuda.synchronize()
+        mx, rms = _stats(got.cpu(), ref)
+        print(f"\n[parity] GIN predictor ragged batch ({'text' if cond is not None else 'dropped'}): max|d|={mx:.4f} rms={rms:.5f} (std {float(ref.std()):.2f})")
+        assert mx <= 0.03 and rms <= 0.006, (mx, rms)
+    # k larger than anything a thread keeps, k == out_dim boundary and k = 1
+    for k in (1, 50, D):
+        probs, idx = gp.topk_templates(x.to(DEV), ei.to(DEV), ea.to(DEV), b.to(DEV), c.to(DEV), k)
+        torch.cuda.synchronize()
+        lg = gp(x.to(DEV), ei.to(DEV), ea.to(DEV), b.to(DEV), c.to(DEV)).float().cpu()
+        tv, ti = torch.topk(torch.softmax(lg, dim=1), k, dim=1)
+        assert torch.allclose(probs.cpu(), tv, atol=1e-5)
+        assert float((torch.gather(torch.softmax(lg, dim=1), 1, idx.cpu().long()) - tv).abs().max()) <= 1e-6
+
+
+@pytest.mark.parametrize("n_list", [[1], [1, 2, 12], [12, 1, 1, 12, 3, 2, 1]])
+def test_dit_degenerate_molecules_vs_oracle(dit_small, n_list):
+    """Molecules of 1 and 2 atoms, a batch of one, and mixed ragged batches: denoiser logits of both guidance halves and a
+    full reverse step (posterior + sampling with pre-drawn noise) against the oracle on the small fixture's weights."""
+    from oracle import llamole_oracle as O
+
+    fx = dit_small
+    P, cfg, meta = fx["params"], fx["cfg"], fx["meta"]
+    N, T = P["max_nodes"], cfg["diffusion_steps"]
+    sd = synth.dit_state_dict(cfg, N, P["w_seed"])
+    d = tempfile.mkdtemp()
+    synth.write_dit_checkpoint(d, cfg, meta, sd)
+    m = GraphDiT(os.path.join(d, "config.yaml"), os.path.join(d, "data.meta.json"), torch.float32)
+    m.init_model(d)
+    m.disable_grads()
+    m = m.to(DEV)
+    B = len(n_list)
+    n_nodes = torch.tensor(n_list)
+    props, txt = synth.dit_conditions(B, seed=17)
+    y = torch.where(props == -200.0, torch.full_like(props, float("nan")), props)
+    node_mask = torch.arange(N)[None, :] < n_nodes[:, None]
+    tb = O.dit_tables(meta)
+    U = O.union_transition(tb)
+    sched = O.cosine_schedule(T)
+    g = torch.Generator().manual_seed(B)
+    ex = lambda *s: torch.empty(*s).exponential_(1.0, generator=g)  # noqa: E731
+    X, E = O.initial_state(tb, node_mask, ex(B, N, 16), ex(B, N, N, 5), torch.float32)
+    eng = m.engine()
+    eng.begin(n_nodes.to(torch.int32), y.to(DEV).contiguous(), txt.to(DEV).contiguous())
+    eng.set_state(*state_from_onehot(X, E))
+    t = T - 1
+    t_norm = torch.full((B, 1), t / T)
+    with torch.no_grad():
+        for unc in (False, True):
+            rX, rE = O.denoiser_forward(sd, cfg, X, E, node_mask, y, txt, t_norm, unc)
+            lX, lE = eng.denoise(t, unc)
+            torch.cuda.synchronize()
+            mx, rms = _stats(torch.cat([lX.cpu().flatten(), lE.cpu().flatten()]), torch.cat([rX.flatten(), rE.flatten()]))
+            assert mx <= 0.10 and rms <= 0.02, (n_list, unc, mx, rms)
+            assert float((lE.cpu() * (rE == 0)).abs().max()) == 0.0
+        qX, qE = ex(B, N, 16), ex(B, N, N, 5)
+        Xn, En, _, _, pX, pE = O.reverse_step(sd, cfg, tb, U, sched, X, E, node_mask, y, txt, t, qX, qE, return_probs=True)
+    eng.set_state(*state_from_onehot(X, E))
+    eng.step(t, 0, qX.to(DEV).contiguous(), qE.to(DEV).contiguous())
+    gX, gE = eng.get_state()
+    torch.cuda.synchronize()
+    rXc, rEc = state_from_onehot(Xn, En)
+    gX, gE = gX.cpu().long(), gE.cpu().long()
+    # structure is exact: masked atoms / pairs, symmetry, diagonal
+    assert torch.equal(gX == -1, rXc.long() == -1) and torch.equal(gE == -1, rEc.long() == -1)
+    assert torch.equal(gE, gE.transpose(1, 2))
+    # categories agree wherever the oracle's decision margin exceeds the logit tolerance
+    mX = _margins(pX, qX, node_mask)
+    agree = (gX == rXc.long())[node_mask]
+    assert bool(agree[mX > 0.35].all()), (n_list, float(agree.float().mean()))
