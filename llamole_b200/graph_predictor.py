@@ -15,6 +15,24 @@ from . import _cabi
 from .gin_engine import GinEngine, _Holder, gin_trunk_skeleton, mlp4
 
 
+_TEMPLATE_BACKEND = None
+
+
+def set_template_backend(fn) -> None:
+    """Override the retro-template application `fn(template, product_smiles) -> list of reactant SMILES`
+    (default: rdchiral.main.rdchiralRunText, as graph_predictor/model.py:191).  None restores the default."""
+    global _TEMPLATE_BACKEND
+    _TEMPLATE_BACKEND = fn
+
+
+def _template_backend():
+    if _TEMPLATE_BACKEND is not None:
+        return _TEMPLATE_BACKEND
+    from rdchiral.main import rdchiralRunText
+
+    return rdchiralRunText
+
+
 class GraphPredictor(nn.Module):
     def __init__(self, num_layer, hidden_size, drop_ratio, out_dim, model_config, label_to_template, available=None):
         super().__init__()
@@ -138,18 +156,50 @@ class GraphPredictor(nn.Module):
     def sample_templates(self, product_graph, c, product_smiles, topk=10):
         """(reactants, scores, templates) sorted by merged score, scores summing to 1; ([],[],[]) if no template applies
         (graph_predictor/model.py:164-228).  The reference's second, discarded predictor pass (c=None) is dropped."""
-        from rdchiral.main import rdchiralRunText
-
         x, edge_index, edge_attr = product_graph.x, product_graph.edge_index, product_graph.edge_attr
         batch = torch.zeros(x.size(0), dtype=torch.long, device=x.device)
         probs, idx = self.topk_templates(x, edge_index, edge_attr, batch, c, topk)
-        probs = probs[0].float().cpu().tolist()
-        idx = idx[0].cpu().tolist()
+        return self._apply_templates(probs[0].float().cpu().tolist(), idx[0].cpu().tolist(), product_smiles)
+
+    def sample_templates_batch(self, product_graphs, c, product_smiles_list, topk=10):
+        """Batched A* expansion: `sample_templates` for MANY products with ONE predictor call.
+
+        The reference expands one open node per planner iteration with a B=1 predictor call (planner/molstar.py:24-71,
+        modeling_llamole.py:784-889); expanding the k best open nodes together turns that into the batched candidate
+        scoring of BASELINE.json configs[3].  `product_graphs` is a list of PyG-like objects (x, edge_index, edge_attr),
+        `c` (len, text_dim) or None, `product_smiles_list` the matching SMILES.  Returns one (reactants, scores,
+        templates) triple per product, each identical to what `sample_templates` returns for that product alone."""
+        if len(product_graphs) != len(product_smiles_list):
+            raise ValueError("product_graphs and product_smiles_list differ in length")
+        if c is not None and c.shape[0] != len(product_graphs):
+            raise ValueError(f"c has {c.shape[0]} rows for {len(product_graphs)} products")
+        if not product_graphs:
+            return []
+        dev = product_graphs[0].x.device
+        xs, eis, eas, bs = [], [], [], []
+        base = 0
+        for gi, g in enumerate(product_graphs):
+            n = int(g.x.size(0))
+            if n == 0:
+                raise ValueError(f"product {gi} has no atoms")
+            xs.append(g.x.reshape(-1))
+            eis.append(g.edge_index + base)
+            eas.append(g.edge_attr.reshape(-1))
+            bs.append(torch.full((n,), gi, dtype=torch.long, device=dev))
+            base += n
+        probs, idx = self.topk_templates(torch.cat(xs), torch.cat(eis, dim=1), torch.cat(eas), torch.cat(bs), c, topk)
+        probs, idx = probs.float().cpu().tolist(), idx.cpu().tolist()
+        return [self._apply_templates(p, i, smi) for p, i, smi in zip(probs, idx, product_smiles_list)]
+
+    def _apply_templates(self, probs, labels, product_smiles):
+        """Host half of sample_templates (graph_predictor/model.py:187-228): apply each of the top-k templates to the
+        product, split a template's probability evenly over its outcomes, merge identical reactant sets."""
+        run = _template_backend()
         found = defaultdict(list)
-        for prob, label in zip(probs, idx):
+        for prob, label in zip(probs, labels):
             template = self.label_to_template[label]
             try:
-                outcomes = sorted(rdchiralRunText(template, product_smiles))
+                outcomes = sorted(run(template, product_smiles))
             except Exception:
                 continue
             for reactant in outcomes:

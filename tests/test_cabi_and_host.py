@@ -123,3 +123,73 @@ def test_synthetic_graphs_follow_the_reference_layout():
     assert bool((b[ei[0]] == b[ei[1]]).all())
     deg = torch.bincount(ei[1], minlength=x.numel())
     assert int(deg.max()) <= 4
+
+
+# ------------------------------------------------------------------------------------------------ template merge (host)
+def _reference_merge(topk_probs, templates, product_smiles, run):
+    """Literal restatement of the host half of the reference's sample_templates (graph_predictor/model.py:187-228)."""
+    from collections import defaultdict
+
+    reactants_d = defaultdict(list)
+    for prob, template in zip(topk_probs, templates):
+        try:
+            outcomes = run(template, product_smiles)
+            if len(outcomes) == 0:
+                continue
+            outcomes = sorted(outcomes)
+            for reactant in outcomes:
+                if "." in reactant:
+                    str_list = sorted(reactant.strip().split("."))
+                    reactants_d[".".join(str_list)].append((prob / len(outcomes), template))
+                else:
+                    reactants_d[reactant].append((prob / len(outcomes), template))
+        except Exception:
+            pass
+    if len(reactants_d) == 0:
+        return [], [], []
+    ret = []
+    for reactant, l in reactants_d.items():
+        ss, ts = zip(*l)
+        ret.append((reactant, sum(ss), list(ts)[0]))
+    reactants, scores, templates = zip(*sorted(ret, key=lambda item: item[1], reverse=True))
+    total = sum(scores)
+    return list(reactants), [s / total for s in scores], list(templates)
+
+
+def _fake_rdchiral(template, smiles):
+    """Deterministic stand-in for rdchiralRunText: outcomes depend on (template, product); some templates do not apply,
+    some raise, several map to the same reactant set written in a different order."""
+    k = int(template[1:])
+    if k % 5 == 0:
+        return []
+    if k % 7 == 0:
+        raise ValueError("template does not parse")
+    if k % 3 == 0:
+        return [f"C{len(smiles)}.N", f"N.C{len(smiles)}", "O"]      # two spellings of one reactant set
+    return [f"C{k % 4}", f"O.C{k % 2}"]
+
+
+def test_template_merge_matches_the_reference_logic():
+    from llamole_b200.graph_predictor import set_template_backend
+
+    gp = GraphPredictor(2, 64, 0.0, 40, {}, {i: f"T{i}" for i in range(40)})
+    set_template_backend(_fake_rdchiral)
+    try:
+        g = torch.Generator().manual_seed(0)
+        for trial in range(20):
+            k = int(torch.randint(1, 12, (1,), generator=g))
+            labels = torch.randperm(40, generator=g)[:k].tolist()
+            probs = torch.rand(k, generator=g).sort(descending=True).values.tolist()
+            smi = "C" * (trial % 5 + 1)
+            got = gp._apply_templates(probs, labels, smi)
+            want = _reference_merge(probs, [gp.label_to_template[i] for i in labels], smi, _fake_rdchiral)
+            assert got[0] == want[0] and got[2] == want[2]
+            assert all(abs(a - b) < 1e-12 for a, b in zip(got[1], want[1]))
+            if got[1]:
+                assert abs(sum(got[1]) - 1.0) < 1e-9
+        assert gp._apply_templates([0.5, 0.5], [0, 5], "CC") == ([], [], [])     # nothing applies
+    finally:
+        set_template_backend(None)
+    with pytest.raises(ValueError):
+        gp.sample_templates_batch([object()], None, ["C", "CC"], 3)
+    assert gp.sample_templates_batch([], None, [], 3) == []

@@ -599,3 +599,45 @@ def test_dit_degenerate_molecules_vs_oracle(dit_small, n_list):
     mX = _margins(pX, qX, node_mask)
     agree = (gX == rXc.long())[node_mask]
     assert bool(agree[mX > 0.35].all()), (n_list, float(agree.float().mean()))
+
+
+def test_batched_expansion_equals_per_product_calls(gin_small):
+    """`sample_templates_batch` over several products (one predictor call) returns, product by
+    product, what the reference-shaped B=1 `sample_templates` returns (rdchiral replaced by a deterministic stand-in)."""
+    from types import SimpleNamespace
+
+    from llamole_b200.graph_predictor import set_template_backend
+
+    fx = gin_small
+    P = fx["params"]
+    d = tempfile.mkdtemp()
+    synth.write_predictor_checkpoint(d, P["L"], P["H"], P["out_dim"], P["pred_seed"], with_cost=False)
+    gp = GraphPredictor(P["L"], P["H"], 0.0, P["out_dim"], {}, {i: f"T{i}" for i in range(P["out_dim"])})
+    gp.init_model(d)
+    gp = gp.to(DEV)
+
+    def run(template, smiles):
+        k = int(template[1:])
+        if k % 5 == 0:
+            return []
+        if k % 3 == 0:
+            return [f"C{len(smiles)}.N", f"N.C{len(smiles)}", "O"]
+        return [f"C{k % 4}", f"O.C{k % 2}"]
+
+    sizes = [1, 9, 30, 2, 17]
+    graphs, smiles = [], []
+    for gi, n in enumerate(sizes):
+        x, ei, ea, _ = synth.molecular_graphs(1, seed=50 + gi, min_nodes=n, max_nodes=n)
+        graphs.append(SimpleNamespace(x=x.to(DEV), edge_index=ei.to(DEV), edge_attr=ea.to(DEV)))
+        smiles.append("C" * n)
+    c = torch.nn.functional.silu(torch.randn(len(sizes), 768, generator=torch.Generator().manual_seed(2))).to(DEV)
+    set_template_backend(run)
+    try:
+        batched = gp.sample_templates_batch(graphs, c, smiles, topk=10)
+        for gi, g in enumerate(graphs):
+            single = gp.sample_templates(g, c[gi:gi + 1], smiles[gi], topk=10)
+            assert batched[gi][0] == single[0] and batched[gi][2] == single[2]
+            assert all(abs(a - b) < 1e-6 for a, b in zip(batched[gi][1], single[1]))
+            assert single[0], "the stand-in backend applies to most templates"
+    finally:
+        set_template_backend(None)
