@@ -5,6 +5,8 @@
 // (bf16 copy: the gather source of the aggregation and nothing else).  Edges are a destination-sorted CSR
 // (rowptr/col/etype), graphs are contiguous node ranges (graph_ptr), so every reduction (neighbour sum,
 // per-graph max / sum pooling) is a segmented loop with no atomics.
+#include <stdlib.h>
+
 #include <vector>
 
 #include "llb_gemm.cuh"
@@ -332,7 +334,8 @@ __device__ __forceinline__ bool tk_before(float v, int i, float w, int j) { retu
 
 __global__ void __launch_bounds__(1024) gin_topk_stream_kernel(const float* __restrict__ logits, int ld, int W, int k,
                                                                float* __restrict__ topv, int32_t* __restrict__ topi,
-                                                               int32_t* __restrict__ redo_flag) {
+                                                               int32_t* __restrict__ redo_flag, int only_flagged) {
+  if (only_flagged && redo_flag[blockIdx.x] == 0) return;   // the threshold kernel already produced this row
   __shared__ float red_v[32];
   __shared__ float red_s[32];
   __shared__ int red_i[32];
@@ -434,6 +437,124 @@ __global__ void __launch_bounds__(1024) gin_topk_stream_kernel(const float* __re
   }
   __syncthreads();
   if (tid == 0) redo_flag[blockIdx.x] = s_redo;
+}
+
+// Threshold variant of the single-pass kernel for WIDE rows (the predictor's 180 576 templates).  In the kernel above
+// every thread maintains its own sorted list, and the insertion branch diverges: a thread inserts ~19 times per row, but
+// some lane of a warp inserts in ~600 of its 176 x 4 element steps, so the warp spends most of the pass in the
+// insertion path (47 us per row instead of the ~7 us the row's bytes need).  Here the block first looks at a strided
+// SAMPLE of 4096 elements (one float4 per thread), takes tau = the R-th largest of the 32 warp maxima (R ~ 7 k 4096 / W,
+// so that ~7 k elements of the row are expected above tau) and m0 = the sample maximum, then streams the row once with
+// a branch-free body -- sum += 2^((v - m0) log2 e), running max -- and pushes the rare elements v > tau into a
+// shared-memory candidate list.  The top k of the row are the top k of the candidates (everything else is <= tau); each
+// candidate finds its rank by counting (value descending, ties to the lower index), no barrier rounds.
+// Exactness: if fewer than k candidates were found, the list overflowed, or the row maximum exceeds m0 by more than
+// 2^60 (overflow guard of the fixed-reference sum), the row is flagged and redone by the kernels above.
+constexpr int TKH_CAP = 2048;
+__device__ __forceinline__ uint32_t tk_enc(float v) {
+  const uint32_t u = __float_as_uint(v);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float tk_dec(uint32_t e) { return __uint_as_float((e & 0x80000000u) ? (e & 0x7fffffffu) : ~e); }
+
+__global__ void __launch_bounds__(1024) gin_topk_thresh_kernel(const float* __restrict__ logits, int ld, int W, int k, int R,
+                                                               float* __restrict__ topv, int32_t* __restrict__ topi,
+                                                               int32_t* __restrict__ redo_flag) {
+  __shared__ uint32_t wkey[32];
+  __shared__ float red_m[32], red_s[32];
+  __shared__ float2 cand[TKH_CAP];   // (value, index bits)
+  __shared__ int s_cnt;
+  const float* row = logits + (size_t)blockIdx.x * ld;
+  const float4* row4 = reinterpret_cast<const float4*>(row);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int W4 = W >> 2;
+  constexpr float LOG2E = 1.4426950408889634f;
+  // ---- sample: float4 number tid * (W4 / 1024), spread over the whole row
+  {
+    const float4 q = __ldg(row4 + (size_t)tid * (W4 >> 10));
+    const uint32_t key = tk_enc(fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w)));
+    const uint32_t wmax = __reduce_max_sync(0xffffffffu, key);
+    if (lane == 0) wkey[warp] = wmax;
+    if (tid == 0) s_cnt = 0;
+  }
+  __syncthreads();
+  float tau, m0;
+  {
+    uint32_t cur = wkey[lane];
+    m0 = tk_dec(__reduce_max_sync(0xffffffffu, cur));
+    uint32_t t = 0;
+    for (int r = 0; r < R; ++r) {   // R-th largest (with multiplicity) of the 32 warp maxima
+      t = __reduce_max_sync(0xffffffffu, cur);
+      const uint32_t holders = __ballot_sync(0xffffffffu, cur == t);
+      if (lane == __ffs(holders) - 1) cur = 0u;   // 0 encodes below every float
+    }
+    tau = tk_dec(t);
+  }
+  // ---- one pass over the row
+  const float m0c = m0 * LOG2E;
+  float ls = 0.f, lm = -INFINITY;
+  auto visit = [&](float v, int c) {
+    ls += ex2_approx(fmaf(v, LOG2E, -m0c));
+    lm = fmaxf(lm, v);
+    if (v > tau) {
+      const int p = atomicAdd(&s_cnt, 1);
+      if (p < TKH_CAP) cand[p] = make_float2(v, __int_as_float(c));
+    }
+  };
+  {
+    int c4 = tid;
+    for (; c4 + 1024 < W4; c4 += 2048) {
+      const float4 q0 = __ldcs(row4 + c4), q1 = __ldcs(row4 + c4 + 1024);   // streamed once: do not keep it in L2
+      visit(q0.x, 4 * c4), visit(q0.y, 4 * c4 + 1), visit(q0.z, 4 * c4 + 2), visit(q0.w, 4 * c4 + 3);
+      visit(q1.x, 4 * c4 + 4096), visit(q1.y, 4 * c4 + 4097), visit(q1.z, 4 * c4 + 4098), visit(q1.w, 4 * c4 + 4099);
+    }
+    for (; c4 < W4; c4 += 1024) {
+      const float4 q = __ldcs(row4 + c4);
+      visit(q.x, 4 * c4), visit(q.y, 4 * c4 + 1), visit(q.z, 4 * c4 + 2), visit(q.w, 4 * c4 + 3);
+    }
+    for (int c = (W4 << 2) + tid; c < W; c += 1024) visit(row[c], c);
+  }
+  const float wm = warp_max(lm), wsum = warp_sum(ls);
+  if (lane == 0) red_m[warp] = wm, red_s[warp] = wsum;
+  __syncthreads();
+  const float m = warp_max(red_m[lane]);
+  const float sum = warp_sum(red_s[lane]);
+  const int C = s_cnt;
+  if (C < k || C > TKH_CAP || (m - m0) * LOG2E > 60.f || !(sum > 0.f)) {   // block-uniform
+    if (tid == 0) redo_flag[blockIdx.x] = 1;
+    return;
+  }
+  const float inv = 1.0f / sum;
+  for (int t = tid; t < C; t += 1024) {
+    const float2 me = cand[t];
+    const int mi = __float_as_int(me.y);
+    int rank = 0;
+    for (int j = 0; j < C; ++j) {
+      const float2 o = cand[j];   // same address for the whole warp: broadcast
+      rank += (o.x > me.x || (o.x == me.x && __float_as_int(o.y) < mi)) ? 1 : 0;
+    }
+    if (rank < k) {
+      topv[(size_t)blockIdx.x * k + rank] = ex2_approx(fmaf(me.x, LOG2E, -m0c)) * inv;
+      topi[(size_t)blockIdx.x * k + rank] = mi;
+    }
+  }
+  if (tid == 0) redo_flag[blockIdx.x] = 0;
+}
+
+// Rows per launch -> (threshold kernel | per-thread-list kernel) -> selection-pass kernel for whatever is still flagged.
+static void launch_softmax_topk(const float* logits, int rows, int W, int ld, int k, float* topv, int32_t* topi, int32_t* flags,
+                                cudaStream_t s) {
+  const bool vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0);
+  const long long r_need = ((long long)7 * k * 4096 + W - 1) / W;
+  const int R = r_need < 4 ? 4 : (int)r_need;
+  static const bool no_thresh = getenv("LLB_TOPK_THRESH") && getenv("LLB_TOPK_THRESH")[0] == '0';
+  if (vec && W >= 16384 && R <= 32 && !no_thresh) {
+    gin_topk_thresh_kernel<<<rows, 1024, 0, s>>>(logits, ld, W, k, R, topv, topi, flags);
+    gin_topk_stream_kernel<<<rows, 1024, 0, s>>>(logits, ld, W, k, topv, topi, flags, 1);
+  } else {
+    gin_topk_stream_kernel<<<rows, 1024, 0, s>>>(logits, ld, W, k, topv, topi, flags, 0);
+  }
+  gin_topk_kernel<<<rows, 1024, 0, s>>>(logits, ld, W, k, topv, topi, flags);
 }
 
 __global__ void cost_mlp_kernel(const float* __restrict__ w0, const float* __restrict__ b0, const float* __restrict__ w1,
@@ -825,12 +946,9 @@ int llb_gin_predictor_topk(llb_gin* g, const float* c, int k, float* topk_prob, 
     LLB_TRY(gemm_bias_act(g->hz + (size_t)r0 * G.HH, G.HH, g->w<void>(G.head4_w), G.HH, g->w<float>(G.head4_b), g->logits_ws, G.out_dim,
                           rows, G.out_dim, G.HH, LLB_ACT_NONE, true, s, &g->ctr));
     ProfScope prof(LLB_PROF_GIN_TOPK, s);
-    gin_topk_stream_kernel<<<rows, 1024, 0, s>>>(g->logits_ws, G.out_dim, G.out_dim, k, topk_prob + (size_t)r0 * k, topk_idx + (size_t)r0 * k,
-                                                 g->topk_redo);
-    gin_topk_kernel<<<rows, 1024, 0, s>>>(g->logits_ws, G.out_dim, G.out_dim, k, topk_prob + (size_t)r0 * k, topk_idx + (size_t)r0 * k,
-                                          g->topk_redo);
+    launch_softmax_topk(g->logits_ws, rows, G.out_dim, G.out_dim, k, topk_prob + (size_t)r0 * k, topk_idx + (size_t)r0 * k, g->topk_redo, s);
     LLB_CUDA_OK(cudaGetLastError());
-    g->launches += 2;
+    g->launches += 3;
   }
   return LLB_OK;
 }
@@ -843,8 +961,7 @@ int llb_softmax_topk(const float* logits, int rows, int W, int ld, int k, float*
   LLB_CHECK_ARG(logits && topk_prob && topk_idx && scratch && rows >= 1 && W >= 1 && ld >= W && k >= 1 && k <= W,
                 "llb_softmax_topk: bad argument (rows=%d W=%d ld=%d k=%d)", rows, W, ld, k);
   cudaStream_t s = (cudaStream_t)stream;
-  gin_topk_stream_kernel<<<rows, 1024, 0, s>>>(logits, ld, W, k, topk_prob, topk_idx, scratch);
-  gin_topk_kernel<<<rows, 1024, 0, s>>>(logits, ld, W, k, topk_prob, topk_idx, scratch);
+  launch_softmax_topk(logits, rows, W, ld, k, topk_prob, topk_idx, scratch, s);
   LLB_CUDA_OK(cudaGetLastError());
   return LLB_OK;
 }

@@ -385,7 +385,12 @@ def test_gin_predictor_matches_reference(gin_small):
 
 # ------------------------------------------------------------------------------------------------ softmax + top-k
 @pytest.mark.parametrize("rows,W,k,case", [(7, 64, 10, "random"), (5, 20000, 50, "random"), (3, 180576, 50, "random"),
-                                           (4, 20000, 50, "one_residue"), (4, 5000, 50, "ties"), (2, 4099, 17, "ragged")])
+                                           (4, 12000, 50, "one_residue"), (4, 5000, 50, "ties"), (2, 4099, 17, "ragged"),
+                                           # wide rows: the threshold kernel and every way it hands a row back
+                                           (3, 180576, 1, "random"), (3, 180576, 200, "random"), (2, 180576, 300, "random"),
+                                           (3, 16384, 50, "random"), (3, 180576, 50, "ties"), (2, 180576, 50, "sorted_desc"),
+                                           (2, 180576, 50, "all_equal"), (3, 180576, 50, "outlier"), (3, 180576, 50, "few_above"),
+                                           (2, 65537, 50, "ragged")])
 def test_softmax_topk_matches_torch(rows, W, k, case):
     """Streaming top-k (and its selection-pass redo) against torch.softmax + a stable sort, bit-exact indices."""
     g = torch.Generator(device="cpu").manual_seed(rows * 31 + W)
@@ -397,6 +402,16 @@ def test_softmax_topk_matches_torch(rows, W, k, case):
             vals[r, torch.tensor([12, 13, 14, 15, 4108, 4109])] = 5.0 + torch.rand(6, generator=g)
     if case == "ties":
         vals = torch.round(vals * 4) / 4    # heavy ties: order must fall back to the lowest index
+    if case == "sorted_desc":
+        vals = vals.sort(dim=1, descending=True).values
+    if case == "all_equal":                 # no element exceeds the threshold: threshold kernel -> list kernel -> selection passes
+        vals = torch.full_like(vals, 0.25)
+    if case == "outlier":                   # row maximum far above the sampled maximum: overflow guard of the fixed-reference sum
+        vals[:, 4 * 7 + 1] = 200.0          # float4 number 7 is not a sampled one (stride W4 / 1024 = 44)
+    if case == "few_above":                 # fewer than k elements above the bulk
+        vals = torch.zeros_like(vals)
+        for r in range(rows):
+            vals[r, torch.randperm(W, generator=g)[:30]] = 1.0 + torch.rand(30, generator=g)
     logits[:, :W] = vals
     d = logits.to(DEV)
     prob = torch.empty(rows, k, device=DEV)
@@ -412,6 +427,8 @@ def test_softmax_topk_matches_torch(rows, W, k, case):
     assert torch.allclose(prob.cpu().double(), torch.gather(p, 1, order), rtol=2e-5, atol=1e-9)
     if case == "one_residue":
         assert int(scratch.sum()) == rows      # every row needed the redo
+    if case in ("all_equal", "few_above") and k <= 64:
+        assert int(scratch.sum()) == rows      # handed down to the selection-pass kernel
 
 
 # ------------------------------------------------------------------------------------------------ condition queue (8f-3)
