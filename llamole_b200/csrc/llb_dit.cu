@@ -313,13 +313,13 @@ static int dit_forward(llb_dit* h, int t, cudaStream_t s) {
   // LLB_FUSED_LN: 0 = GEMM + row kernel; 1 = fused, 4-CTA cluster kernel (projection only: with K = 4 H its single-CTA
   // main loop loses more than the row kernel costs); 2 = cluster kernel for both halves; 3 (default) = fused on the
   // CTA-pair main loop for both halves when H = 1024, else as 1.
-  // LLB_ATTN: 1 = mma.sync kernel with register-staged loads; 3 = the same with TMA-delivered operands;
-  // 2 = tcgen05 kernel (two heads per 128-row tile; needs an even head count)
+  // LLB_ATTN: 1 = mma.sync kernel with register-staged loads; 3 (default) = the same with TMA-delivered operands;
+  // 2 = tcgen05 kernel (two heads per 128-row tile, P in tensor memory; needs an even head count)
   static int attn_env = -1;
   if (attn_env < 0) {
     const char* v = getenv("LLB_ATTN");
     int mode = (v && v[0] >= '1' && v[0] <= '3') ? v[0] - '0' : LLB_ATTN_DEFAULT;
-    if (mode == 2 && cudaFuncSetAttribute(dit_attention_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTU_SMEM) != cudaSuccess) {
+    if (mode == 2 && cudaFuncSetAttribute(dit_attention_umma4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT4_SMEM) != cudaSuccess) {
       (void)cudaGetLastError();
       mode = 1;
     }
@@ -327,7 +327,6 @@ static int dit_forward(llb_dit* h, int t, cudaStream_t s) {
   }
   const bool attn_umma = attn_env == 2 && L.heads % 2 == 0 && L.N <= 64;
   const bool attn_tma = attn_env == 3 && L.N <= 64;
-  static const int attn_dbg = getenv("LLB_ATTN_DBG") ? atoi(getenv("LLB_ATTN_DBG")) : 0;   // timing experiments only
   const int ln_mode = gemm_ln_mode();
   const bool fused_pair = fused_ln && (ln_mode == 3 || ln_mode == 4) && H == 4 * GLN_BN;   // 4 = pair kernel, projection only
   const bool fused_fc2 = ln_mode == 2 || (fused_pair && ln_mode == 3);
@@ -348,8 +347,8 @@ static int dit_forward(llb_dit* h, int t, cudaStream_t s) {
         ProfScope prof(LLB_PROF_ATTENTION, s);
         if (attn_umma) {
           const int units = seqs * (L.heads / 2);
-          dit_attention_umma_kernel<<<units < num_sms() ? units : num_sms(), ATTU_THREADS, ATTU_SMEM, s>>>(tmQKV, h->attn, h->mol_off, B, Mtok, H,
-                                                                                                            L.heads, units, attn_dbg);
+          dit_attention_umma4_kernel<<<units < num_sms() ? units : num_sms(), ATT4_THREADS, ATT4_SMEM, s>>>(tmQKV, h->attn, h->mol_off, B, Mtok, H,
+                                                                                                            L.heads, units);
         } else {
           dit_attention_tma_kernel<<<(unsigned)(seqs * L.heads), 128, 0, s>>>(tmQKV, h->attn, h->mol_off, B, Mtok, H, L.heads);
         }

@@ -191,8 +191,8 @@ __global__ void __launch_bounds__(128) dit_attention_kernel(const __nv_bfloat16*
   uint32_t p[8][2];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float e0 = exp2f(s[j][0] - m0), e1 = exp2f(s[j][1] - m0);
-    const float e2 = exp2f(s[j][2] - m1), e3 = exp2f(s[j][3] - m1);
+    const float e0 = ex2_approx(s[j][0] - m0), e1 = ex2_approx(s[j][1] - m0);   // MUFU.EX2 alone: exp2f adds a range fix-up per call
+    const float e2 = ex2_approx(s[j][2] - m1), e3 = ex2_approx(s[j][3] - m1);
     l0 += e0 + e1;
     l1 += e2 + e3;
     p[j][0] = pack_bf16x2(e0, e1);
@@ -319,8 +319,8 @@ __global__ void __launch_bounds__(128) dit_attention_tma_kernel(const __grid_con
   uint32_t p[8][2];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float e0 = exp2f(s[j][0] - m0), e1 = exp2f(s[j][1] - m0);
-    const float e2 = exp2f(s[j][2] - m1), e3 = exp2f(s[j][3] - m1);
+    const float e0 = ex2_approx(s[j][0] - m0), e1 = ex2_approx(s[j][1] - m0);   // MUFU.EX2 alone: exp2f adds a range fix-up per call
+    const float e2 = ex2_approx(s[j][2] - m1), e3 = ex2_approx(s[j][3] - m1);
     l0 += e0 + e1;
     l1 += e2 + e3;
     p[j][0] = pack_bf16x2(e0, e1);
@@ -371,53 +371,59 @@ __global__ void __launch_bounds__(128) dit_attention_tma_kernel(const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------------
-// Attention on tcgen05 (default when the head count is even).  The mma.sync kernel above is bound by the shared-memory
-// pipe: every warp re-reads K and V with ldmatrix and the loads themselves go global -> registers -> shared.  Here the
-// tensor core reads its operands straight from the tiles TMA wrote:
+// Attention on tcgen05 (LLB_ATTN=2, opt-in; needs an even head count).  The mma.sync kernels above re-read K and V with
+// ldmatrix in every warp; here the tensor core reads its operands straight from the tiles TMA wrote:
 //   unit      = (sequence, pair of heads).  Q2 / K2 / V2 are 128-row tiles: rows 0..63 head h0, rows 64..127 head h1
 //               (six 64 x 64 TMA boxes of the qkv matrix, 128-byte swizzle; rows past the sequence end belong to the
 //               next sequence or are zero-filled, and are masked).
 //   S         = Q2 . K2^T  (M128 x N128 x K64, fp32 in TMEM): the two diagonal 64 x 64 blocks are the two heads' scores.
 //   softmax   = thread r owns row r: tcgen05.ld of its block's 64 columns, exp2 (q carries dh^-0.5 log2 e), masked keys
-//               contribute exactly 0, bf16 row -> the block-diagonal P tile (K-major, swizzled; the off-diagonal
-//               blocks stay zero from the start).
-//   O         = P . V2 (M128 x N64 x K128): V2 is consumed as an MN-major operand, i.e. exactly the [key][dh] tile TMA
-//               delivered, no transposition.  O / row-sum -> bf16 -> coalesced masked stores.
-// Persistent CTA, 6 warps: 0..3 softmax + epilogue (thread = TMEM lane = row), 4 TMA producer (3-stage ring), 5 MMA issuer.
+//               contribute exactly 0.
+//   P         never touches shared memory: the bf16 row of the block-diagonal P goes back into TENSOR memory, columns
+//               [0,64) of the unit's 128 (32-bit column c = keys 2c, 2c+1 of the stacked 128 keys; the other head's half
+//               is written as zeros).  A first design staged P in swizzled shared memory (64 KB of P tiles, 192 TMEM
+//               columns per unit): two units in flight per SM, 18.8 ms/step.
+//   O         = P . V2 (M128 x N64 x K128) is a tcgen05.mma with the A operand in tensor memory and V2 as an MN-major
+//               shared-memory operand (exactly the [key][dh] tile TMA delivered, no transposition); it lands in columns
+//               [64,128), which S no longer needs.  O / row-sum -> bf16 -> each thread stores its row's 128 bytes.
+// Four units are in flight (4 x 128 columns), fed by a 4-stage ring of 48 KB TMA stages; 16 softmax / epilogue warps
+// (4 per unit), one TMA warp, one MMA warp that issues S of unit k, then P V of unit k - 2.
+// Measured: 15.2 ms/step (335 us per launch under ncu, 60 % DRAM, issue slots 59 % busy) against 13.2 ms for the
+// TMA-fed mma.sync kernel; with molecules of 5..50 atoms the fixed 128-row unit costs more (11.4 vs 8.1 ms/step).
 // ------------------------------------------------------------------------------------------------
-constexpr int ATTU_STAGES = 3;
 constexpr int ATTU_TILE = 128 * 64 * 2;                       // one 128-row operand tile (16 KB)
 constexpr int ATTU_STAGE_BYTES = 3 * ATTU_TILE;               // Q2 | K2 | V2
-constexpr int ATTU_OFF_P = ATTU_STAGES * ATTU_STAGE_BYTES;    // per softmax group: two K-halves of [128 rows][64 keys] bf16
-constexpr int ATTU_OFF_BARS = ATTU_OFF_P + 2 * 2 * ATTU_TILE;
-constexpr int ATTU_SMEM = ATTU_OFF_BARS + 256 + 1024;
-constexpr int ATTU_THREADS = 320;                             // 2 softmax groups x 4 warps, TMA producer, MMA issuer
+constexpr int ATT4_STAGES = 4;
+constexpr int ATT4_GROUPS = 4;
+constexpr int ATT4_OFF_BARS = ATT4_STAGES * ATTU_STAGE_BYTES;
+constexpr int ATT4_SMEM = ATT4_OFF_BARS + 512 + 1024;
+constexpr int ATT4_THREADS = (4 * ATT4_GROUPS + 2) * 32;
 
-__global__ void __launch_bounds__(ATTU_THREADS, 1)
-dit_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ out, const int32_t* __restrict__ mol_off,
-                          int B, int Mtok, int H, int heads, int num_units, int dbg) {
-  extern __shared__ uint8_t attu_raw[];
-  uint8_t* smem = attu_raw + ((1024u - (smem_u32(attu_raw) & 1023u)) & 1023u);
-  uint8_t* smP = smem + ATTU_OFF_P;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATTU_OFF_BARS);
-  uint64_t* full = bars;                      // [STAGES] TMA -> MMA
-  uint64_t* empty = bars + ATTU_STAGES;       // [STAGES] MMA (P V done) -> TMA
-  uint64_t* s_full = bars + 2 * ATTU_STAGES;  // [2] S of the group's unit is in TMEM
-  uint64_t* p_full = s_full + 2;              // [2] P is in shared memory (and S consumed)
-  uint64_t* o_full = s_full + 4;              // [2] O is in TMEM
-  uint64_t* o_empty = s_full + 6;             // [2] O consumed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 8);
+__global__ void __launch_bounds__(ATT4_THREADS, 1)
+dit_attention_umma4_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ out, const int32_t* __restrict__ mol_off,
+                           int B, int Mtok, int H, int heads, int num_units) {
+  extern __shared__ uint8_t att4_raw[];
+  uint8_t* smem = att4_raw + ((1024u - (smem_u32(att4_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT4_OFF_BARS);
+  uint64_t* full = bars;                        // [STAGES] TMA -> MMA
+  uint64_t* empty = full + ATT4_STAGES;         // [STAGES] P V done -> TMA
+  uint64_t* s_full = empty + ATT4_STAGES;       // [GROUPS] S in TMEM
+  uint64_t* p_full = s_full + ATT4_GROUPS;      // [GROUPS] P in TMEM (and S consumed)
+  uint64_t* o_full = p_full + ATT4_GROUPS;      // [GROUPS] O in TMEM
+  uint64_t* o_empty = o_full + ATT4_GROUPS;     // [GROUPS] O consumed: the unit's 128 columns are free
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + ATT4_GROUPS);
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
   const int hpairs = heads >> 1;
+  constexpr int W_TMA = 4 * ATT4_GROUPS, W_MMA = W_TMA + 1;
 
-  if (warp == 8 && elect_one()) {
+  if (warp == W_TMA && elect_one()) {
     tma_prefetch_desc(&tmQKV);
-    for (int i = 0; i < ATTU_STAGES; ++i) {
+    for (int i = 0; i < ATT4_STAGES; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
-    for (int g = 0; g < 2; ++g) {
+    for (int g = 0; g < ATT4_GROUPS; ++g) {
       mbar_init(&s_full[g], 1);
       mbar_init(&p_full[g], 4);
       mbar_init(&o_full[g], 1);
@@ -425,16 +431,13 @@ dit_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat
     }
     fence_mbar_init();
   }
-  if (warp == 9) tmem_alloc(tmem_slot, 512);
-  // the off-diagonal blocks of P are never written: zero both groups' tiles once
-  for (int i = threadIdx.x; i < 4 * ATTU_TILE / 16; i += ATTU_THREADS) reinterpret_cast<uint4*>(smP)[i] = make_uint4(0, 0, 0, 0);
-  fence_proxy_async_smem();
+  if (warp == W_MMA) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == W_TMA) {
     // ---------------- TMA producer ----------------
     int st = 0;
     uint32_t ph = 0;
@@ -455,67 +458,61 @@ dit_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat
             tma_load_2d(base + mat * ATTU_TILE + hl * (ATTU_TILE / 2), &tmQKV, &full[st], mat * H + (2 * hp + hl) * DIT_DH, row0);
       }
       __syncwarp();
-      if (++st == ATTU_STAGES) {
+      if (++st == ATT4_STAGES) {
         st = 0;
         ph ^= 1;
       }
     }
-  } else if (warp == 9) {
-    // ---------------- MMA issuer: S of unit k, then P V of unit k - 1 (the other group's softmax runs in between) ----------------
+  } else if (warp == W_MMA) {
+    // ---------------- MMA issuer ----------------
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128);
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64) | (1u << 16);   // B (= V2) is MN-major
-    const uint64_t p_desc0 = umma_desc_k128(smem_u32(smP));
-    auto issue_pv = [&](int g, uint32_t gph, int st) {
-      mbar_wait(&p_full[g], gph);
-      mbar_wait(&o_empty[g], gph ^ 1);
+    auto issue_pv = [&](int j) {   // unit j of this CTA: group j & 3, stage j & 3, use number j >> 2 of both
+      const int g = j & 3, st = j & 3;
+      mbar_wait(&p_full[g], (uint32_t)((j >> 2) & 1));
       tc_fence_after();
       if (elect_one()) {
-        const uint64_t p_desc = p_desc0 + (uint64_t)(g * 2 * (ATTU_TILE >> 4));
+        const uint32_t t_p = tmem_base + g * 128, t_o = t_p + 64;
         const uint64_t v_desc = umma_desc_k128(smem_u32(smem + st * ATTU_STAGE_BYTES + 2 * ATTU_TILE));
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk)   // 16 keys per step: P K-half kk / 4, 32 bytes along its rows; V2 16 rows = 2 KB further down
-          umma_bf16(tmem_base + g * 256 + 128, p_desc + (uint64_t)((kk >> 2) * (ATTU_TILE >> 4) + (kk & 3) * 2), v_desc + (uint64_t)(kk * 128), idesc_o,
-                    kk != 0 ? 1u : 0u);
+        for (int kk = 0; kk < 8; ++kk)   // 16 keys per step: 8 columns of P; V2 16 rows = 2 KB further down
+          umma_bf16_ts(t_o, t_p + kk * 8, v_desc + (uint64_t)(kk * 128), idesc_o, kk != 0 ? 1u : 0u);
         umma_commit(&o_full[g]);
         umma_commit(&empty[st]);
       }
       __syncwarp();
     };
-    int k = 0, st = 0, prev_st = 0;
-    uint32_t ph = 0;
+    int k = 0;
     for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
       const int seq = u / hpairs;
       const int b = seq % B;
       if (mol_off[b + 1] - mol_off[b] == 0) continue;
-      const int g = k & 1;
+      const int g = k & 3, st = k & 3;
+      const uint32_t use = (uint32_t)((k >> 2) & 1);
       const uint64_t q_desc = umma_desc_k128(smem_u32(smem + st * ATTU_STAGE_BYTES));
       const uint64_t k_desc = q_desc + (ATTU_TILE >> 4);
-      mbar_wait(&full[st], ph);
+      mbar_wait(&full[st], use);
+      mbar_wait(&o_empty[g], use ^ 1);   // the previous unit of this group has read its O: the 128 columns are free
       tc_fence_after();
       if (elect_one()) {
 #pragma unroll
-        for (int kq = 0; kq < 4; ++kq) umma_bf16(tmem_base + g * 256, q_desc + 2 * kq, k_desc + 2 * kq, idesc_s, kq != 0 ? 1u : 0u);
+        for (int kq = 0; kq < 4; ++kq) umma_bf16(tmem_base + g * 128, q_desc + 2 * kq, k_desc + 2 * kq, idesc_s, kq != 0 ? 1u : 0u);
         umma_commit(&s_full[g]);
       }
       __syncwarp();
-      if (k > 0) issue_pv(g ^ 1, (uint32_t)(((k - 1) >> 1) & 1), prev_st);
-      prev_st = st;
+      if (k >= 2) issue_pv(k - 2);
       ++k;
-      if (++st == ATTU_STAGES) {
-        st = 0;
-        ph ^= 1;
-      }
     }
-    if (k > 0) issue_pv((k - 1) & 1, (uint32_t)(((k - 1) >> 1) & 1), prev_st);
+    if (k >= 2) issue_pv(k - 2);
+    if (k >= 1) issue_pv(k - 1);
   } else {
     // ---------------- softmax + epilogue: group = warp / 4, thread = row of the stacked 128-row tile ----------------
     const int grp = warp >> 2, wq = warp & 3;
     const int r = wq * 32 + lane;            // TMEM lane
-    const int hl = r >> 6;                   // head of the pair
-    const uint32_t t_s = tmem_base + ((uint32_t)(wq * 32) << 16) + grp * 256 + hl * 64;
-    const uint32_t t_o = tmem_base + ((uint32_t)(wq * 32) << 16) + grp * 256 + 128;
-    const uint32_t pbase = smem_u32(smP) + grp * 2 * ATTU_TILE;
-    const uint32_t prow = pbase + hl * ATTU_TILE + r * 128;   // this row's 128 bytes inside its diagonal block
+    const int hl = wq >> 1;                  // head of the pair (warp-uniform)
+    const uint32_t t_grp = tmem_base + ((uint32_t)(wq * 32) << 16) + grp * 128;
+    const uint32_t t_s = t_grp + hl * 64;
+    const uint32_t t_o = t_grp + 64;
     int k = 0;
     uint32_t up = 0;
     for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
@@ -523,7 +520,7 @@ dit_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat
       const int b = seq % B, pass = seq / B;
       const int n = mol_off[b + 1] - mol_off[b];
       if (n == 0) continue;
-      if (((k++) & 1) != grp) continue;      // the other group's unit
+      if (((k++) & 3) != grp) continue;      // another group's unit
       const int row0 = pass * Mtok + mol_off[b];
       mbar_wait(&s_full[grp], up);
       tc_fence_after();
@@ -535,19 +532,22 @@ dit_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat
 #pragma unroll
       for (int j = 0; j < 64; ++j) m = fmaxf(m, j < n ? sc[j] : -INFINITY);
       float l = 0.f;
+      const uint32_t zeros[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        float e[8];
+      for (int c = 0; c < 2; ++c) {          // 32 keys -> 16 packed columns per store
+        uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          e[i] = (c * 8 + i < n) ? ((dbg & 2) ? 1.0f : exp2f(sc[c * 8 + i] - m)) : 0.f;
-          l += e[i];
+        for (int i = 0; i < 16; ++i) {
+          const int j = c * 32 + 2 * i;
+          const float e0 = j < n ? ex2_approx(sc[j] - m) : 0.f;
+          const float e1 = j + 1 < n ? ex2_approx(sc[j + 1] - m) : 0.f;
+          l += e0 + e1;
+          pk[i] = pack_bf16x2(e0, e1);
         }
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + ((c ^ (r & 7)) << 4)), "r"(pack_bf16x2(e[0], e[1])),
-                     "r"(pack_bf16x2(e[2], e[3])), "r"(pack_bf16x2(e[4], e[5])), "r"(pack_bf16x2(e[6], e[7]))
-                     : "memory");
+        tmem_st16(t_grp + hl * 32 + c * 16, pk);
+        tmem_st16(t_grp + (1 - hl) * 32 + c * 16, zeros);
       }
-      fence_proxy_async_smem();
+      tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[grp]);
@@ -560,35 +560,20 @@ dit_attention_umma_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_empty[grp]);
-      if (dbg & 4) { up ^= 1; continue; }
-      // stage the normalised bf16 row in this row's (now idle) P slot, then 8 lanes write one 128-byte row segment
+      const int q_idx = r & 63;
+      if (q_idx < n) {
+        uint4* dst = reinterpret_cast<uint4*>(out + (size_t)(row0 + q_idx) * H + (2 * hp + hl) * DIT_DH);
 #pragma unroll
-      for (int c = 0; c < 8; ++c)
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + ((c ^ (r & 7)) << 4)),
-                     "r"(pack_bf16x2(sc[c * 8] * inv, sc[c * 8 + 1] * inv)), "r"(pack_bf16x2(sc[c * 8 + 2] * inv, sc[c * 8 + 3] * inv)),
-                     "r"(pack_bf16x2(sc[c * 8 + 4] * inv, sc[c * 8 + 5] * inv)), "r"(pack_bf16x2(sc[c * 8 + 6] * inv, sc[c * 8 + 7] * inv))
-                     : "memory");
-      __syncwarp();
-      const int whl = (wq * 32) >> 6;                               // the warp's 32 rows all belong to one head
-      const uint32_t wbase = pbase + whl * ATTU_TILE + (wq * 32) * 128;
-      __nv_bfloat16* obase = out + (size_t)row0 * H + (2 * hp + whl) * DIT_DH;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int pp = lane + 32 * i;
-        const int rr = pp >> 3, ch = pp & 7;
-        const int q_idx = ((wq * 32) & 63) + rr;
-        uint4 v4;
-        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v4.x), "=r"(v4.y), "=r"(v4.z), "=r"(v4.w)
-                     : "r"(wbase + rr * 128 + ((ch ^ ((wq * 32 + rr) & 7)) << 4)));
-        if (q_idx < n && !(dbg & 1)) *reinterpret_cast<uint4*>(obase + (size_t)q_idx * H + ch * 8) = v4;
+        for (int c = 0; c < 8; ++c)
+          dst[c] = make_uint4(pack_bf16x2(sc[c * 8] * inv, sc[c * 8 + 1] * inv), pack_bf16x2(sc[c * 8 + 2] * inv, sc[c * 8 + 3] * inv),
+                              pack_bf16x2(sc[c * 8 + 4] * inv, sc[c * 8 + 5] * inv), pack_bf16x2(sc[c * 8 + 6] * inv, sc[c * 8 + 7] * inv));
       }
-      __syncwarp();   // the staged rows are read before the group's next unit overwrites them with P
       up ^= 1;
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == W_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
