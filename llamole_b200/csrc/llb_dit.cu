@@ -66,8 +66,8 @@ int make_layout(const llb_dit_config& c, DitLayout& L) {
     L.proj_w.push_back(take(H * H * 2));
     L.fc1_w.push_back(take(F * H * 2));
     L.fc2_w.push_back(take(H * F * 2));
-    L.ada2_w.push_back(take(6 * H * H * 2));
   }
+  for (size_t l = 0; l < D; ++l) L.ada2_w.push_back(take(6 * H * H * 2));   // contiguous: one (D 6H, H) operand of the grouped launch
   L.x_ln_w = take(H * 4), L.x_ln_b = take(H * 4);
   L.ada0_b = take((D + 1) * H * 4);
   L.out_fc1_b = take(H * 4), L.out_fc2_b = take((size_t)L.d0 * 4), L.out_ada2_b = take((size_t)2 * L.d0 * 4);
@@ -75,8 +75,8 @@ int make_layout(const llb_dit_config& c, DitLayout& L) {
     L.qn_w.push_back(take(DIT_DH * 4)), L.qn_b.push_back(take(DIT_DH * 4));
     L.kn_w.push_back(take(DIT_DH * 4)), L.kn_b.push_back(take(DIT_DH * 4));
     L.proj_b.push_back(take(H * 4)), L.fc1_b.push_back(take(F * 4)), L.fc2_b.push_back(take(H * 4));
-    L.ada2_b.push_back(take(6 * H * 4));
   }
+  for (size_t l = 0; l < D; ++l) L.ada2_b.push_back(take(6 * H * 4));   // contiguous, like the weights
   L.y_mlp0_w = take((size_t)L.ydim * H * 4), L.y_mlp0_b = take((size_t)L.ydim * H * 4), L.y_drop = take((size_t)L.ydim * H * 4);
   L.txt_drop = take(H * 4), L.txt_b = take(H * 4);
   L.c1_table = take((size_t)(L.T + 1) * H * 4);
@@ -296,9 +296,20 @@ static int dit_forward(llb_dit* h, int t, cudaStream_t s) {
   ctr->slot = LLB_PROF_GEMM_ADALN;
   const int ldh = (D + 1) * H;
   LLB_TRY(gemm_bias_act(h->cvec, H, h->w<void>(L.ada0_w), H, h->w<float>(L.ada0_b), h->hid, ldh, B + 1, ldh, H, LLB_ACT_SILU, false, s, ctr));
-  for (int l = 0; l < D; ++l)
-    LLB_TRY(gemm_bias_act(h->hid + (size_t)l * H, ldh, h->w<void>(L.ada2_w[l]), H, h->w<float>(L.ada2_b[l]),
-                          h->mod + (size_t)l * (B + 1) * 6 * H, 6 * H, B + 1, 6 * H, H, LLB_ACT_SOFTSIGN, true, s, ctr));
+  // the D modulation linears depend only on the condition: ONE launch grouped along N (group l reads hid[:, l H : (l+1) H],
+  // its 6H x H weight is rows [l 6H, (l+1) 6H) of the stacked operand); mod is (B+1, D, 6H).  LLB_ADALN_GROUPED=0: D launches.
+  static const bool adaln_split = getenv("LLB_ADALN_GROUPED") && getenv("LLB_ADALN_GROUPED")[0] == '0';
+  const int ldm = D * 6 * H;
+  if (!adaln_split && (6 * H) % 256 == 0) {
+    GemmGroups grp;
+    grp.group_n = 6 * H, grp.group_k = H;
+    LLB_TRY(gemm_bias_act(h->hid, ldh, h->w<void>(L.ada2_w[0]), H, h->w<float>(L.ada2_b[0]), h->mod, ldm, B + 1, ldm, H, LLB_ACT_SOFTSIGN, true, s,
+                          ctr, grp));
+  } else {
+    for (int l = 0; l < D; ++l)
+      LLB_TRY(gemm_bias_act(h->hid + (size_t)l * H, ldh, h->w<void>(L.ada2_w[l]), H, h->w<float>(L.ada2_b[l]), h->mod + (size_t)l * 6 * H, ldm,
+                            B + 1, 6 * H, H, LLB_ACT_SOFTSIGN, true, s, ctr));
+  }
   LLB_TRY(gemm_bias_act(h->hid + (size_t)D * H, ldh, h->w<void>(L.out_ada2_w), H, h->w<float>(L.out_ada2_b), h->modout, 2 * L.d0,
                         B + 1, 2 * L.d0, H, LLB_ACT_NONE, true, s, ctr));
   // 3. transformer blocks
@@ -332,7 +343,7 @@ static int dit_forward(llb_dit* h, int t, cudaStream_t s) {
   const bool fused_fc2 = ln_mode == 2 || (fused_pair && ln_mode == 3);
   const size_t ln_sync_bytes = gemm_ln_pair_workspace_bytes();
   for (int l = 0; l < D; ++l) {
-    const float* mod = h->mod + (size_t)l * (B + 1) * 6 * H;
+    const float* mod = h->mod + (size_t)l * 6 * H;   // row stride ldm
     // Block 0 sees the SAME token embedding in the conditional and the unconditional half and attention has no
     // conditioning, so its qkv GEMM and attention run once on Mtok rows; the halves part ways at the first modulation.
     const bool share0 = l == 0 && h->passes == 2 && fused_ln;
@@ -362,9 +373,9 @@ static int dit_forward(llb_dit* h, int t, cudaStream_t s) {
     // x += gate * (LN(linear(.)) (1 + scale) + shift): fused into the GEMM epilogue when a cluster can hold a full row
     RowLnArgs a;
     a.in = h->y, a.in_ld = H, a.in_bf16 = true, a.rows = M, a.width = H;
-    a.row_group = h->row_group, a.mod_ld = 6 * H;
+    a.row_group = h->row_group, a.mod_ld = ldm;
     a.resid = h->x, a.resid_ld = H, a.out_f32 = h->x, a.out_f32_ld = H, a.out_bf16 = h->xb, a.out_bf16_ld = H;
-    GemmLnArgs f{nullptr, h->row_group, nullptr, nullptr, nullptr, 6 * H, h->x, H, h->xb, H};
+    GemmLnArgs f{nullptr, h->row_group, nullptr, nullptr, nullptr, ldm, h->x, H, h->xb, H};
     ctr->slot = LLB_PROF_GEMM_PROJ;
     if (fused_ln) {
       f.bias = h->w<float>(L.proj_b[l]), f.shift = mod, f.scale = mod + H, f.gate = mod + 2 * H;

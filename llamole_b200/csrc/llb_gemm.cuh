@@ -135,7 +135,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const Epi& epi, const CUtenso
 template <int BN, bool TMA_STORE, class Epi>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmC, int M, int N, int K, Epi epi) {
+                    const __grid_constant__ CUtensorMap tmC, int M, int N, int K, Epi epi, int group_n, int group_k) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int ELEM = Epi::OUT_F32 ? 4 : 2;
@@ -187,11 +187,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / num_n) * GEMM_BM;
       const int n0 = (tile % num_n) * BN;
+      const int ka0 = group_n > 0 ? (n0 / group_n) * group_k : 0;   // grouped along N: group g reads A columns [g group_k, +K)
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
-          tma_load_2d(smA + stage * Cfg::A_BYTES, &tmA, &full[stage], kb * GEMM_BK, m0);
+          tma_load_2d(smA + stage * Cfg::A_BYTES, &tmA, &full[stage], ka0 + kb * GEMM_BK, m0);
           tma_load_2d(smB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * GEMM_BK, n0);
         }
         __syncwarp();
@@ -329,7 +330,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
 template <bool TMA_STORE, class Epi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const __grid_constant__ CUtensorMap tmC, int M, int N, int K, Epi epi) {
+                         const __grid_constant__ CUtensorMap tmC, int M, int N, int K, Epi epi, int group_n, int group_k) {
   using Cfg = Gemm2Cfg;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int BN = Cfg::BN;
@@ -388,6 +389,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++tcount) {
       const int m0 = (tile / num_n) * (2 * GEMM_BM) + rank * GEMM_BM;
       const int n0 = (tile % num_n) * BN + rank * (BN / 2);
+      const int ka0 = group_n > 0 ? (n0 / group_n) * group_k : 0;   // grouped along N (group_n is a multiple of BN)
       long long wsum = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
 #ifdef LLB_GEMM_TRACE
@@ -400,7 +402,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #endif
         if (elect_one()) {
           if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
-          tma_load_2d_2sm(smA + stage * Cfg::A_BYTES, &tmA, &full[stage], kb * GEMM_BK, m0);
+          tma_load_2d_2sm(smA + stage * Cfg::A_BYTES, &tmA, &full[stage], ka0 + kb * GEMM_BK, m0);
           tma_load_2d_2sm(smB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * GEMM_BK, n0);
         }
         __syncwarp();
@@ -507,6 +509,13 @@ int make_tensor_map_2d(CUtensorMap* out, const void* ptr, int elem_bytes, int ro
 
 bool gemm_pair_enabled();   // LLB_GEMM_PAIR=0 forces the single-CTA kernel (debug / A-B comparison)
 
+// Grouped along N (group_n > 0): output columns [g group_n, (g+1) group_n) are A[:, g group_k : g group_k + K] . W[g group_n ..]^T,
+// i.e. G independent linears that share their rows, with their (N_g, K) weights stacked and their inputs side by side --
+// one launch instead of G (the 28 adaLN modulation linears of a reverse step).
+struct GemmGroups {
+  int group_n = 0, group_k = 0;
+};
+
 struct GemmCounters {
   int64_t launches = 0;
   int slot = LLB_PROF_GEMM_OTHER;  // profiling slot charged for the next launches
@@ -514,7 +523,7 @@ struct GemmCounters {
 
 template <int BN, class Epi>
 int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const Epi& epi,
-                cudaStream_t stream, GemmCounters* ctr = nullptr) {
+                cudaStream_t stream, GemmCounters* ctr = nullptr, GemmGroups grp = GemmGroups()) {
   using Cfg = GemmCfg<BN>;
   if (M <= 0 || N <= 0) return LLB_OK;
   LLB_CHECK_ARG(K > 0 && lda % 8 == 0 && ldw % 8 == 0, "gemm: K=%d lda=%d ldw=%d (ld must be a multiple of 8)", K, lda, ldw);
@@ -522,7 +531,10 @@ int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, in
                 "gemm: operands must be 16-byte aligned");
   constexpr int ELEM = Epi::OUT_F32 ? 4 : 2;
   CUtensorMap tmA, tmB, tmC;
-  LLB_TRY(make_tensor_map_2d(&tmA, A, 2, M, K, lda, GEMM_BK, GEMM_BM, 128));
+  LLB_CHECK_ARG(grp.group_n == 0 || (grp.group_n % 256 == 0 && grp.group_k >= K && grp.group_k % 8 == 0 && N % grp.group_n == 0),
+                "gemm: grouped call needs group_n=%d a multiple of 256 dividing N=%d and group_k=%d >= K", grp.group_n, N, grp.group_k);
+  const int a_cols = grp.group_n ? (N / grp.group_n - 1) * grp.group_k + K : K;
+  LLB_TRY(make_tensor_map_2d(&tmA, A, 2, M, a_cols, lda, GEMM_BK, GEMM_BM, 128));
   LLB_TRY(make_tensor_map_2d(&tmB, W, 2, N, K, ldw, GEMM_BK, BN, 128));
   const bool tma_store = ((size_t)epi.ldc * ELEM) % 16 == 0 && (reinterpret_cast<uintptr_t>(epi.C) & 15) == 0;
   if (tma_store) LLB_TRY(make_tensor_map_2d(&tmC, epi.C, ELEM, M, N, epi.ldc, Epi::CHUNK, 32, Epi::CHUNK * ELEM));
@@ -543,7 +555,7 @@ int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, in
       }
       const int pairs = pair_tiles < num_sms() / 2 ? pair_tiles : num_sms() / 2;
       ProfScope prof(ctr ? ctr->slot : LLB_PROF_GEMM_OTHER, stream);
-      kern<<<2 * pairs, GEMM_THREADS, Gemm2Cfg::SMEM_BYTES, stream>>>(tmA, tmBh, tmC, M, N, K, epi);
+      kern<<<2 * pairs, GEMM_THREADS, Gemm2Cfg::SMEM_BYTES, stream>>>(tmA, tmBh, tmC, M, N, K, epi, grp.group_n, grp.group_k);
       return LLB_OK;
     };
     if (tma_store) LLB_TRY(launch2(gemm_tcgen05_2cta_kernel<true, Epi>, 2));
@@ -555,7 +567,7 @@ int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, in
         configured[which] = true;
       }
       ProfScope prof(ctr ? ctr->slot : LLB_PROF_GEMM_OTHER, stream);
-      kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, M, N, K, epi);
+      kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, M, N, K, epi, grp.group_n, grp.group_k);
       return LLB_OK;
     };
     if (tma_store) LLB_TRY(launch(gemm_tcgen05_kernel<BN, true, Epi>, 0));
@@ -612,6 +624,6 @@ struct EpiBiasAct {
 
 // Generic runtime-dispatched GEMM used by the small / non-critical linears.
 int gemm_bias_act(const void* A, int lda, const void* W, int ldw, const float* bias, void* C, int ldc, int M, int N,
-                  int K, int act, bool out_f32, cudaStream_t stream, GemmCounters* ctr = nullptr);
+                  int K, int act, bool out_f32, cudaStream_t stream, GemmCounters* ctr = nullptr, GemmGroups grp = GemmGroups());
 
 }  // namespace llb

@@ -893,7 +893,9 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (tr) GLN_TRACE(tcount, 3, clock64());
       // poll this row's four mailboxes (one per column slice) until all carry this tile's tag
       {
-        float s = 0.f, ss = 0.f;
+        // the partial sums are kept per source and added in slice order once all four are in: adding them in ARRIVAL
+        // order made the fp32 row statistics -- and through them a few sampled categories per step -- vary from run to run
+        float sv[NS], ssv[NS];
         uint32_t pending = 0xFu;
         const long long start = clock64();
         while (pending) {
@@ -902,7 +904,7 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (pending & (1u << src)) {
               const uint4 v = ld_mailbox(gstats + src * GEMM_BM + rloc);
               if (v.y == tag && v.w == tag) {
-                s += __uint_as_float(v.x), ss += __uint_as_float(v.z);
+                sv[src] = __uint_as_float(v.x), ssv[src] = __uint_as_float(v.z);
                 pending &= ~(1u << src);
               }
             }
@@ -913,6 +915,9 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
         if (tr) GLN_TRACE(tcount, 4, clock64());
+        float s = 0.f, ss = 0.f;
+#pragma unroll
+        for (int src = 0; src < NS; ++src) s += sv[src], ss += ssv[src];
         const float mean = s * inv_n;
         const float var = fmaxf(ss * inv_n - mean * mean, 0.0f);
         a.rstd = rsqrtf(var + 1e-5f);

@@ -191,33 +191,33 @@ static int pick_bn(int M, int N) {
 
 template <int ACT, bool F32>
 static int gemm_dispatch_bn(const void* A, int lda, const void* W, int ldw, const float* bias, void* C, int ldc, int M,
-                            int N, int K, cudaStream_t stream, GemmCounters* ctr) {
+                            int N, int K, cudaStream_t stream, GemmCounters* ctr, GemmGroups grp) {
   LLB_CHECK_ARG(bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0, "gemm: bias must be 16-byte aligned");
   EpiBiasAct<ACT, F32> epi{C, ldc, bias};
   switch (pick_bn(M, N)) {
-    case 256: return launch_gemm<256>(A, lda, W, ldw, M, N, K, epi, stream, ctr);
-    case 128: return launch_gemm<128>(A, lda, W, ldw, M, N, K, epi, stream, ctr);
-    default: return launch_gemm<64>(A, lda, W, ldw, M, N, K, epi, stream, ctr);
+    case 256: return launch_gemm<256>(A, lda, W, ldw, M, N, K, epi, stream, ctr, grp);
+    case 128: return launch_gemm<128>(A, lda, W, ldw, M, N, K, epi, stream, ctr, grp);
+    default: return launch_gemm<64>(A, lda, W, ldw, M, N, K, epi, stream, ctr, grp);
   }
 }
 
 template <bool F32>
 static int gemm_dispatch_act(const void* A, int lda, const void* W, int ldw, const float* bias, void* C, int ldc, int M,
-                             int N, int K, int act, cudaStream_t stream, GemmCounters* ctr) {
+                             int N, int K, int act, cudaStream_t stream, GemmCounters* ctr, GemmGroups grp) {
   switch (act) {
-    case LLB_ACT_NONE: return gemm_dispatch_bn<LLB_ACT_NONE, F32>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, ctr);
-    case LLB_ACT_GELU: return gemm_dispatch_bn<LLB_ACT_GELU, F32>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, ctr);
-    case LLB_ACT_SILU: return gemm_dispatch_bn<LLB_ACT_SILU, F32>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, ctr);
+    case LLB_ACT_NONE: return gemm_dispatch_bn<LLB_ACT_NONE, F32>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, ctr, grp);
+    case LLB_ACT_GELU: return gemm_dispatch_bn<LLB_ACT_GELU, F32>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, ctr, grp);
+    case LLB_ACT_SILU: return gemm_dispatch_bn<LLB_ACT_SILU, F32>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, ctr, grp);
     case LLB_ACT_SOFTSIGN:
-      return gemm_dispatch_bn<LLB_ACT_SOFTSIGN, F32>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, ctr);
+      return gemm_dispatch_bn<LLB_ACT_SOFTSIGN, F32>(A, lda, W, ldw, bias, C, ldc, M, N, K, stream, ctr, grp);
   }
   return fail(LLB_ERR_INVALID, "gemm: unknown activation %d", act);
 }
 
 int gemm_bias_act(const void* A, int lda, const void* W, int ldw, const float* bias, void* C, int ldc, int M, int N,
-                  int K, int act, bool out_f32, cudaStream_t stream, GemmCounters* ctr) {
-  return out_f32 ? gemm_dispatch_act<true>(A, lda, W, ldw, bias, C, ldc, M, N, K, act, stream, ctr)
-                 : gemm_dispatch_act<false>(A, lda, W, ldw, bias, C, ldc, M, N, K, act, stream, ctr);
+                  int K, int act, bool out_f32, cudaStream_t stream, GemmCounters* ctr, GemmGroups grp) {
+  return out_f32 ? gemm_dispatch_act<true>(A, lda, W, ldw, bias, C, ldc, M, N, K, act, stream, ctr, grp)
+                 : gemm_dispatch_act<false>(A, lda, W, ldw, bias, C, ldc, M, N, K, act, stream, ctr, grp);
 }
 
 }  // namespace llb
