@@ -10,6 +10,10 @@ group when one is initialised) and hands each request its own slice of the resul
 Determinism contract: molecule i of the queue (in submission order since construction) is sampled with the counter RNG
 keyed by the GLOBAL index `index_base + i`, and its node count comes from a generator keyed the same way, so a
 request's result does not depend on what else was queued with it, on `max_batch`, or on the number of GPUs.
+This is bit-exact as long as the runs being compared use the same block-tail kernels: below 2048 token rows per rank the
+sampler switches to its latency-regime kernels, whose fp32 rounding differs in the last place from
+the fused throughput kernels, so a request sampled alone in a tiny batch and the same request inside a large one agree
+except on decisions whose margin is at that rounding level (~1e-6 of the decisions).  Set LLB_FUSED_LN to pin one mode.
 """
 from __future__ import annotations
 
