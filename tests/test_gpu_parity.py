@@ -693,3 +693,14 @@ def test_sampler_is_deterministic_on_the_fused_throughput_path():
         else:
             assert torch.equal(cur[0], ref[0]) and torch.equal(cur[1], ref[1]), f"repeat {rep}: sampled graphs differ"
             assert torch.equal(cur[2], ref[2]) and torch.equal(cur[3], ref[3]), f"repeat {rep}: logits differ"
+    # ... and independent of batch composition on the same path: the tail of the batch sampled on its own (still >= 2048
+    # token rows) with its global molecule indices reproduces the corresponding rows exactly
+    cut = 64
+    eng.begin(n_nodes[cut:], props[cut:].contiguous(), txt[cut:].to(DEV).contiguous(), mol_index_base=cut)
+    assert 2 * int(n_nodes[cut:].sum()) >= 2048
+    eng.init_state(11, None, None)
+    for i in range(6):
+        eng.step(T - i, 11)
+    X, E = eng.get_state()
+    torch.cuda.synchronize()
+    assert torch.equal(X, ref[0][cut:]) and torch.equal(E, ref[1][cut:])
