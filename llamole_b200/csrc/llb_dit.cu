@@ -5,6 +5,9 @@
 
 #include <vector>
 
+// split-K factor of the latency-regime fc2 (K = F): F / 4 per slice, partial products summed by the row kernel
+#define LLB_DIT_SPLITK 4
+
 #ifndef LLB_ATTN_DEFAULT
 #define LLB_ATTN_DEFAULT 3
 #endif
@@ -74,7 +77,8 @@ int make_layout(const llb_dit_config& c, DitLayout& L) {
   for (size_t l = 0; l < D; ++l) {
     L.qn_w.push_back(take(DIT_DH * 4)), L.qn_b.push_back(take(DIT_DH * 4));
     L.kn_w.push_back(take(DIT_DH * 4)), L.kn_b.push_back(take(DIT_DH * 4));
-    L.proj_b.push_back(take(H * 4)), L.fc1_b.push_back(take(F * 4)), L.fc2_b.push_back(take(H * 4));
+    L.proj_b.push_back(take(H * 4)), L.fc1_b.push_back(take(F * 4));
+    L.fc2_b.push_back(take(LLB_DIT_SPLITK * H * 4));   // H values, then zeros: bias of the split-K launch (slice 0 carries it)
   }
   for (size_t l = 0; l < D; ++l) L.ada2_b.push_back(take(6 * H * 4));   // contiguous, like the weights
   L.y_mlp0_w = take((size_t)L.ydim * H * 4), L.y_mlp0_b = take((size_t)L.ydim * H * 4), L.y_drop = take((size_t)L.ydim * H * 4);
@@ -208,6 +212,7 @@ struct llb_dit {
   __nv_bfloat16* hid = nullptr;  // (B+1,(D+1)H)
   float* mod = nullptr;          // (D, B+1, 6H)
   float* modout = nullptr;       // (B+1, 2 d0)
+  float* part = nullptr;         // (min(2M, 640), SPLITK, H) split-K partial products of fc2
   float* cinv = nullptr;         // (B,H)
   __nv_bfloat16* acond = nullptr;  // (B,KC)
   uint8_t* missing = nullptr;    // (B, ydim+1)
@@ -254,6 +259,7 @@ static int dit_carve(llb_dit* h, void* ws, size_t ws_bytes, int B, int Mtok, siz
   h->row_mol = a.take<int32_t>(Mtok > 0 ? Mtok : 1);
   h->row_group = a.take<int32_t>(M > 0 ? M : 1);
   h->ln_sync = a.take<uint8_t>(gemm_ln_pair_workspace_bytes());
+  h->part = a.take<float>((M < 640 ? M : 640) * (size_t)LLB_DIT_SPLITK * L.H);   // split-K partials (latency regime, <= 640 rows)
   *need = align_up(a.off, 256);
   return LLB_OK;
 }
@@ -401,9 +407,26 @@ static int dit_forward(llb_dit* h, int t, cudaStream_t s) {
       if (fused_pair) LLB_TRY(launch_gemm_ln_pair(h->hbuf, F, h->w<void>(L.fc2_w[l]), F, M, H, F, f, h->ln_sync, ln_sync_bytes, s, ctr));
       else LLB_TRY(launch_gemm_ln(h->hbuf, F, h->w<void>(L.fc2_w[l]), F, M, H, F, f, s, ctr));
     } else {
-      LLB_TRY(gemm_bias_act(h->hbuf, F, h->w<void>(L.fc2_w[l]), F, h->w<float>(L.fc2_b[l]), h->y, H, M, H, F, LLB_ACT_NONE, false, s, ctr));
-      a.shift = mod + 3 * H, a.scale = mod + 4 * H, a.gate = mod + 5 * H;
-      LLB_TRY(launch_row_ln(a, s));
+      // latency regime: K = F is cut into LLB_DIT_SPLITK slices that run as groups of one launch (4x the CTAs streaming the
+      // weights, a quarter of the k-blocks each); the row kernel adds the fp32 partial products in slice order
+      static const bool no_splitk = getenv("LLB_SPLITK") && getenv("LLB_SPLITK")[0] == '0';
+      const int Ks = F / LLB_DIT_SPLITK;
+      // measured: 406 rows 2.16 -> 2.05 ms/step, 978 rows 2.40 -> 2.42 (enough row tiles to fill the machine already)
+      const bool splitk = latency_regime && !no_splitk && F % LLB_DIT_SPLITK == 0 && Ks % 64 == 0 && H % 128 == 0 && M <= 640;
+      if (splitk) {
+        GemmGroups grp;
+        grp.group_n = H, grp.group_k = Ks, grp.split_k = true;
+        LLB_TRY(gemm_bias_act(h->hbuf, F, h->w<void>(L.fc2_w[l]), F, h->w<float>(L.fc2_b[l]), h->part, LLB_DIT_SPLITK * H, M, LLB_DIT_SPLITK * H,
+                              Ks, LLB_ACT_NONE, true, s, ctr, grp));
+        RowLnArgs ap = a;
+        ap.in = h->part, ap.in_ld = LLB_DIT_SPLITK * H, ap.in_bf16 = false, ap.in_parts = LLB_DIT_SPLITK, ap.in_part_stride = H;
+        ap.shift = mod + 3 * H, ap.scale = mod + 4 * H, ap.gate = mod + 5 * H;
+        LLB_TRY(launch_row_ln(ap, s));
+      } else {
+        LLB_TRY(gemm_bias_act(h->hbuf, F, h->w<void>(L.fc2_w[l]), F, h->w<float>(L.fc2_b[l]), h->y, H, M, H, F, LLB_ACT_NONE, false, s, ctr));
+        a.shift = mod + 3 * H, a.scale = mod + 4 * H, a.gate = mod + 5 * H;
+        LLB_TRY(launch_row_ln(a, s));
+      }
       h->launches++;
     }
   }
@@ -485,6 +508,7 @@ int llb_dit_pack_weights(const llb_dit_config* cfg, const llb_dit_weights* w, vo
     LLB_CUDA_OK(cp(L.proj_b[l], w->proj_b[l], H));
     LLB_CUDA_OK(cp(L.fc1_b[l], w->fc1_b[l], F));
     LLB_CUDA_OK(cp(L.fc2_b[l], w->fc2_b[l], H));
+    LLB_CUDA_OK(cudaMemsetAsync(static_cast<uint8_t*>(packed) + L.fc2_b[l] + H * 4, 0, (size_t)(LLB_DIT_SPLITK - 1) * H * 4, s));
     LLB_CUDA_OK(cp(L.ada2_b[l], w->ada2_b[l], 6 * H));
   }
   LLB_TRY(launch_f32_to_bf16(w->out_ada0_w, H, bf(L.ada0_w) + (size_t)D * H * H, H, H, H, H, s));

@@ -135,7 +135,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const Epi& epi, const CUtenso
 template <int BN, bool TMA_STORE, class Epi>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmC, int M, int N, int K, Epi epi, int group_n, int group_k) {
+                    const __grid_constant__ CUtensorMap tmC, int M, int N, int K, Epi epi, int group_n, int group_k, int group_w) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int ELEM = Epi::OUT_F32 ? 4 : 2;
@@ -187,13 +187,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / num_n) * GEMM_BM;
       const int n0 = (tile % num_n) * BN;
-      const int ka0 = group_n > 0 ? (n0 / group_n) * group_k : 0;   // grouped along N: group g reads A columns [g group_k, +K)
+      // grouped along N: group g reads A columns [g group_k, +K); split-K flavour (group_w): it also reads the SAME W rows
+      // at columns [g group_k, +K), i.e. the groups are the K-slices of one linear and C holds their partial products
+      const int grp_i = group_n > 0 ? n0 / group_n : 0;
+      const int ka0 = grp_i * group_k;
+      const int kw0 = group_w ? ka0 : 0, wn0 = group_w ? n0 - grp_i * group_n : n0;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
           tma_load_2d(smA + stage * Cfg::A_BYTES, &tmA, &full[stage], ka0 + kb * GEMM_BK, m0);
-          tma_load_2d(smB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * GEMM_BK, n0);
+          tma_load_2d(smB + stage * Cfg::B_BYTES, &tmB, &full[stage], kw0 + kb * GEMM_BK, wn0);
         }
         __syncwarp();
         if (++stage == STAGES) {
@@ -330,7 +334,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
 template <bool TMA_STORE, class Epi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const __grid_constant__ CUtensorMap tmC, int M, int N, int K, Epi epi, int group_n, int group_k) {
+                         const __grid_constant__ CUtensorMap tmC, int M, int N, int K, Epi epi, int group_n, int group_k, int group_w) {
   using Cfg = Gemm2Cfg;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int BN = Cfg::BN;
@@ -389,7 +393,9 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++tcount) {
       const int m0 = (tile / num_n) * (2 * GEMM_BM) + rank * GEMM_BM;
       const int n0 = (tile % num_n) * BN + rank * (BN / 2);
-      const int ka0 = group_n > 0 ? (n0 / group_n) * group_k : 0;   // grouped along N (group_n is a multiple of BN)
+      const int grp_i = group_n > 0 ? n0 / group_n : 0;   // grouped along N (group_n is a multiple of BN), see the single-CTA kernel
+      const int ka0 = grp_i * group_k;
+      const int kw0 = group_w ? ka0 : 0, wn0 = group_w ? n0 - grp_i * group_n : n0;
       long long wsum = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
 #ifdef LLB_GEMM_TRACE
@@ -403,7 +409,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         if (elect_one()) {
           if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
           tma_load_2d_2sm(smA + stage * Cfg::A_BYTES, &tmA, &full[stage], ka0 + kb * GEMM_BK, m0);
-          tma_load_2d_2sm(smB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * GEMM_BK, n0);
+          tma_load_2d_2sm(smB + stage * Cfg::B_BYTES, &tmB, &full[stage], kw0 + kb * GEMM_BK, wn0);
         }
         __syncwarp();
         if (++stage == STAGES) {
@@ -512,8 +518,11 @@ bool gemm_pair_enabled();   // LLB_GEMM_PAIR=0 forces the single-CTA kernel (deb
 // Grouped along N (group_n > 0): output columns [g group_n, (g+1) group_n) are A[:, g group_k : g group_k + K] . W[g group_n ..]^T,
 // i.e. G independent linears that share their rows, with their (N_g, K) weights stacked and their inputs side by side --
 // one launch instead of G (the 28 adaLN modulation linears of a reverse step).
+// split_k: the groups are the K-slices of ONE linear (W is (group_n, G group_k); group g multiplies A[:, g group_k : +K] with
+// W[:, g group_k : +K]) and C (M, G group_n) holds the G partial products, to be summed by the consumer in a fixed order.
 struct GemmGroups {
   int group_n = 0, group_k = 0;
+  bool split_k = false;
 };
 
 struct GemmCounters {
@@ -531,11 +540,14 @@ int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, in
                 "gemm: operands must be 16-byte aligned");
   constexpr int ELEM = Epi::OUT_F32 ? 4 : 2;
   CUtensorMap tmA, tmB, tmC;
-  LLB_CHECK_ARG(grp.group_n == 0 || (grp.group_n % 256 == 0 && grp.group_k >= K && grp.group_k % 8 == 0 && N % grp.group_n == 0),
-                "gemm: grouped call needs group_n=%d a multiple of 256 dividing N=%d and group_k=%d >= K", grp.group_n, N, grp.group_k);
+  LLB_CHECK_ARG(grp.group_n == 0 || (grp.group_n % BN == 0 && grp.group_k >= K && grp.group_k % 8 == 0 && N % grp.group_n == 0),
+                "gemm: grouped call needs group_n=%d a multiple of the N tile %d dividing N=%d and group_k=%d >= K", grp.group_n, BN, N,
+                grp.group_k);
+  LLB_CHECK_ARG(!grp.split_k || grp.group_n > 0, "gemm: split_k needs groups");
   const int a_cols = grp.group_n ? (N / grp.group_n - 1) * grp.group_k + K : K;
+  const int w_rows = grp.split_k ? grp.group_n : N, w_cols = grp.split_k ? a_cols : K;
   LLB_TRY(make_tensor_map_2d(&tmA, A, 2, M, a_cols, lda, GEMM_BK, GEMM_BM, 128));
-  LLB_TRY(make_tensor_map_2d(&tmB, W, 2, N, K, ldw, GEMM_BK, BN, 128));
+  LLB_TRY(make_tensor_map_2d(&tmB, W, 2, w_rows, w_cols, ldw, GEMM_BK, BN, 128));
   const bool tma_store = ((size_t)epi.ldc * ELEM) % 16 == 0 && (reinterpret_cast<uintptr_t>(epi.C) & 15) == 0;
   if (tma_store) LLB_TRY(make_tensor_map_2d(&tmC, epi.C, ELEM, M, N, epi.ldc, Epi::CHUNK, 32, Epi::CHUNK * ELEM));
   else tmC = tmA;
@@ -544,10 +556,10 @@ int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, in
   static bool configured[4] = {false, false, false, false};  // per template instantiation
   // CTA-pair kernel: wide problems whose 256 x 256 pair-tiles fill the machine
   const int pair_tiles = ceil_div(M, 2 * GEMM_BM) * ceil_div(N, 256);
-  const bool use_pair = BN == 256 && gemm_pair_enabled() && pair_tiles >= num_sms() / 2;
+  const bool use_pair = BN == 256 && gemm_pair_enabled() && pair_tiles >= num_sms() / 2 && grp.group_n % 256 == 0;
   if (use_pair) {
     CUtensorMap tmBh;
-    LLB_TRY(make_tensor_map_2d(&tmBh, W, 2, N, K, ldw, GEMM_BK, 128, 128));
+    LLB_TRY(make_tensor_map_2d(&tmBh, W, 2, w_rows, w_cols, ldw, GEMM_BK, 128, 128));
     auto launch2 = [&](auto kern, int which) -> int {
       if (!configured[which]) {
         LLB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::SMEM_BYTES));
@@ -555,7 +567,7 @@ int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, in
       }
       const int pairs = pair_tiles < num_sms() / 2 ? pair_tiles : num_sms() / 2;
       ProfScope prof(ctr ? ctr->slot : LLB_PROF_GEMM_OTHER, stream);
-      kern<<<2 * pairs, GEMM_THREADS, Gemm2Cfg::SMEM_BYTES, stream>>>(tmA, tmBh, tmC, M, N, K, epi, grp.group_n, grp.group_k);
+      kern<<<2 * pairs, GEMM_THREADS, Gemm2Cfg::SMEM_BYTES, stream>>>(tmA, tmBh, tmC, M, N, K, epi, grp.group_n, grp.group_k, grp.split_k ? 1 : 0);
       return LLB_OK;
     };
     if (tma_store) LLB_TRY(launch2(gemm_tcgen05_2cta_kernel<true, Epi>, 2));
@@ -567,7 +579,7 @@ int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, in
         configured[which] = true;
       }
       ProfScope prof(ctr ? ctr->slot : LLB_PROF_GEMM_OTHER, stream);
-      kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, M, N, K, epi, grp.group_n, grp.group_k);
+      kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, M, N, K, epi, grp.group_n, grp.group_k, grp.split_k ? 1 : 0);
       return LLB_OK;
     };
     if (tma_store) LLB_TRY(launch(gemm_tcgen05_kernel<BN, true, Epi>, 0));

@@ -6,7 +6,7 @@ namespace {
 
 struct RowLnDev {
   const void* in;
-  int in_ld, in_bf16, rows, width, normalize;
+  int in_ld, in_bf16, rows, width, normalize, in_parts, in_part_stride;
   const float *gamma, *beta;
   const int32_t* row_group;
   const float *shift, *scale, *gate;
@@ -133,6 +133,13 @@ __global__ void __launch_bounds__(256) row_ln_reg_kernel(RowLnDev a) {
   float4 v[NCH];
 #pragma unroll
   for (int k = 0; k < NCH; ++k) v[k] = load4(a.in, in_bf16, in_off + lane * 4 + k * 128);
+  for (int p = 1; p < a.in_parts; ++p) {   // split-K partial products, summed in index order
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const float4 q = load4(a.in, in_bf16, in_off + (size_t)p * a.in_part_stride + lane * 4 + k * 128);
+      v[k].x += q.x, v[k].y += q.y, v[k].z += q.z, v[k].w += q.w;
+    }
+  }
   // the residual is fetched together with the row (one exposed DRAM latency per row)
   constexpr int NRES = (NCH <= 8 && !RT && (F & F_RESID)) ? NCH : 1;
   float4 res[NRES];
@@ -261,7 +268,9 @@ int launch_row_ln(const RowLnArgs& a, cudaStream_t stream) {
   if (a.rows <= 0) return LLB_OK;
   LLB_CHECK_ARG(a.width % 4 == 0 && a.in_ld % 4 == 0, "row_ln: width %d / ld %d must be multiples of 4", a.width, a.in_ld);
   LLB_CHECK_ARG((a.shift == nullptr) == (a.scale == nullptr), "row_ln: shift and scale come together");
-  RowLnDev d{a.in, a.in_ld, a.in_bf16 ? 1 : 0, a.rows, a.width, a.normalize ? 1 : 0, a.gamma, a.beta, a.row_group,
+  LLB_CHECK_ARG(a.in_parts >= 1 && (a.in_parts == 1 || (a.width % 128 == 0 && a.in_part_stride % 4 == 0)),
+                "row_ln: summed input parts need a width that is a multiple of 128 (width %d, parts %d)", a.width, a.in_parts);
+  RowLnDev d{a.in, a.in_ld, a.in_bf16 ? 1 : 0, a.rows, a.width, a.normalize ? 1 : 0, a.in_parts, a.in_part_stride, a.gamma, a.beta, a.row_group,
              a.shift, a.scale, a.gate, a.mod_ld, a.act, a.resid, a.resid_ld, a.addvec, a.addvec_ld, a.out_f32,
              a.out_f32_ld, a.out_bf16, a.out_bf16_ld, a.dup_rows, a.l2_normalize ? 1 : 0};
   ProfScope prof(a.prof_slot, stream);

@@ -11,6 +11,8 @@ struct RowLnArgs {
   const void* in = nullptr;
   int in_ld = 0;
   bool in_bf16 = false;
+  int in_parts = 1;          // the input row is the sum of in_parts pieces, in_part_stride elements apart (split-K partials),
+  int in_part_stride = 0;    // added in index order
   int rows = 0, width = 0;
   bool normalize = true;
   const float* gamma = nullptr;

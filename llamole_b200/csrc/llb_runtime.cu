@@ -171,7 +171,7 @@ int make_tensor_map_2d(CUtensorMap* out, const void* ptr, int elem_bytes, int ro
 }
 
 // Pick the N tile: fewest "tile-column units" per SM wave, with a mild preference for the wide tile.
-static int pick_bn(int M, int N) {
+static int pick_bn(int M, int N, int group_n = 0) {
   const int sms = num_sms();
   const int mt = ceil_div(M, GEMM_BM);
   int best = 256;
@@ -179,6 +179,7 @@ static int pick_bn(int M, int N) {
   const int cand[3] = {256, 128, 64};
   const double ineff[3] = {1.0, 1.08, 1.3};
   for (int i = 0; i < 3; ++i) {
+    if (group_n > 0 && group_n % cand[i] != 0) continue;   // a tile must not straddle two groups
     const int tiles = mt * ceil_div(N, cand[i]);
     const double cost = (double)ceil_div(tiles, sms) * cand[i] * ineff[i];
     if (cost < best_cost) {
@@ -194,7 +195,7 @@ static int gemm_dispatch_bn(const void* A, int lda, const void* W, int ldw, cons
                             int N, int K, cudaStream_t stream, GemmCounters* ctr, GemmGroups grp) {
   LLB_CHECK_ARG(bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0, "gemm: bias must be 16-byte aligned");
   EpiBiasAct<ACT, F32> epi{C, ldc, bias};
-  switch (pick_bn(M, N)) {
+  switch (pick_bn(M, N, grp.group_n)) {
     case 256: return launch_gemm<256>(A, lda, W, ldw, M, N, K, epi, stream, ctr, grp);
     case 128: return launch_gemm<128>(A, lda, W, ldw, M, N, K, epi, stream, ctr, grp);
     default: return launch_gemm<64>(A, lda, W, ldw, M, N, K, epi, stream, ctr, grp);
