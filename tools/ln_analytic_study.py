@@ -1,0 +1,55 @@
+"""CPU numerics study (no GPU): can the LayerNorm of the GIN MLP (H -> 4H -> H) take its row statistics ANALYTICALLY, so that
+LN + GELU move into the first GEMM epilogue and the 4H-wide intermediate never goes to HBM un-normalised?
+  mean_i = a_i . wbar + bbar,   E[z^2]_i = (a_i^T G a_i + 2 a_i . (W^T b) + |b|^2) / 4H  with G = W^T W  (one extra H x H GEMM per layer)
+Prints the error of GELU(LN(z)) under fp32 / bf16 / bf16 hi+lo G against the two-pass LayerNorm, next to the bf16 rounding
+error of that output itself.  Result on the synthetic encoder weights: bf16 G costs 3.9e-5 rms, 25x below
+the output rounding."""
+import sys, torch
+sys.path.insert(0,'/root/repo')
+from llamole_b200 import synth
+torch.manual_seed(0)
+L,H=5,768
+enc,proj=synth.gin_encoder_state_dicts(L,H,seed=11)
+x,ei,ea,b=synth.molecular_graphs(256,seed=0)
+bf=lambda t: t.to(torch.bfloat16).to(torch.float32)
+# MLP input of layer 0 as the kernel sees it (bf16 operand)
+h = enc["atom_encoder.weight"][x] + enc["virtualnode_embedding.weight"][0]
+pre="convs.0."
+keys=[k for k in enc if k.startswith(pre)]
+print(keys)
+eps=enc[pre+"eps"]
+bond=enc[pre+"bond_encoder.weight"] if pre+"bond_encoder.weight" in enc else None
+msg=torch.nn.functional.gelu(bf(h)[ei[0]] + bond[ea])
+agg=(1+eps)*h
+agg=agg.index_add(0,ei[1],msg)
+A=bf(agg)
+W1=bf(enc[pre+"mlp.0.weight"]); b1=enc[pre+"mlp.0.bias"]
+gam=enc[pre+"mlp.1.weight"]; bet=enc[pre+"mlp.1.bias"]
+z=A@W1.t()+b1
+N=z.shape[1]
+mu=z.mean(1); var=z.var(1,unbiased=False)
+ref=torch.nn.functional.gelu(torch.nn.functional.layer_norm(z,(N,),gam,bet,1e-5))
+def report(name,mu_a,var_a):
+    rstd=(var+1e-5).rsqrt(); rstd_a=(var_a.clamp_min(0)+1e-5).rsqrt()
+    out=torch.nn.functional.gelu(((z-mu_a[:,None])*rstd_a[:,None])*gam+bet)
+    e=(out-ref).abs()
+    bf_err=(bf(ref)-ref).abs()
+    print(f"{name}: mean rel err {float(((mu_a-mu).abs()/var.sqrt()).max()):.2e} (in sigmas), rstd rel err max {float(((rstd_a-rstd)/rstd).abs().max()):.2e}; "
+          f"output max|d| {float(e.max()):.2e} rms {float(e.pow(2).mean().sqrt()):.2e}  (bf16 rounding of the output itself: max {float(bf_err.max()):.2e} rms {float(bf_err.pow(2).mean().sqrt()):.2e})")
+wbar=W1.mean(0); bbar=b1.mean()
+mu_a=A@wbar+bbar
+G=(W1.t()@W1)            # (H,H) fp32
+c=W1.t()@b1
+def ez2(Gm):
+    return ((A@Gm)*A).sum(1)/N + 2*(A@c)/N + (b1*b1).sum()/N
+report("fp32 G", mu_a, ez2(G)-mu_a**2)
+report("bf16 G", mu_a, ez2(bf(G))-mu_a**2)
+Ghi=bf(G); Glo=bf(G-Ghi)
+report("bf16 hi+lo G", mu_a, ((A@Ghi)*A).sum(1)/N+((A@Glo)*A).sum(1)/N + 2*(A@c)/N + (b1*b1).sum()/N - mu_a**2)
+# centred form: var = a^T Gc a / N + ... with Gc = W1c^T W1c (rows of W1 centred over the output dimension) -> no cancellation
+W1c=W1-wbar[None,:]; b1c=b1-bbar
+Gc=W1c.t()@W1c; cc=W1c.t()@b1c
+def var_c(Gm): return ((A@Gm)*A).sum(1)/N + 2*(A@cc)/N + (b1c*b1c).sum()/N
+report("centred fp32 Gc", mu_a, var_c(Gc))
+report("centred bf16 Gc", mu_a, var_c(bf(Gc)))
+print("z std per row (median)", float(var.sqrt().median()), "mean |mu|", float(mu.abs().mean()))
