@@ -15,6 +15,7 @@
 // so a busy epilogue can never starve the single thread that feeds the tensor pipe.
 // Tiles are walked n-fastest so that the CTAs in flight share A tiles through L2 and W stays L2-resident.
 #pragma once
+#include <type_traits>
 #include "llb_common.cuh"
 
 namespace llb {
@@ -63,6 +64,12 @@ __device__ int g_gemm_exp = 0;
 #define LLB_EXP(bit) false
 #endif
 
+// Epilogue functors that only reduce (no C matrix) declare `static constexpr bool NO_STORE = true`.
+template <class E, class = void>
+struct epi_no_store : std::false_type {};
+template <class E>
+struct epi_no_store<E, std::void_t<decltype(E::NO_STORE)>> : std::integral_constant<bool, E::NO_STORE> {};
+
 // One epilogue warp's share of a 128 x BN accumulator tile: warp % 4 selects the TMEM lane quarter (32 rows), the
 // warps sharing a quarter split the columns.  tcgen05.ld -> fused functor -> swizzled smem staging -> TMA store.
 template <int BN, bool TMA_STORE, class Epi>
@@ -85,7 +92,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const Epi& epi, const CUtenso
     if (Epi::CHUNK == 64) tmem_ld32(t_row + c + 32, v + 32);
     tmem_ld_wait();
     if (!LLB_EXP(4)) epi.transform(row, col0, v, M, N);
-    if (LLB_EXP(8)) continue;
+    if (LLB_EXP(8) || epi_no_store<Epi>::value) continue;
     if (TMA_STORE) {
       uint8_t* dst = stg + buf * (32 * ROW_BYTES);
       if (elect_one()) bulk_wait_read<NBUF - 1>();   // the buffer about to be overwritten has been read out
@@ -548,7 +555,7 @@ int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, in
   const int w_rows = grp.split_k ? grp.group_n : N, w_cols = grp.split_k ? a_cols : K;
   LLB_TRY(make_tensor_map_2d(&tmA, A, 2, M, a_cols, lda, GEMM_BK, GEMM_BM, 128));
   LLB_TRY(make_tensor_map_2d(&tmB, W, 2, w_rows, w_cols, ldw, GEMM_BK, BN, 128));
-  const bool tma_store = ((size_t)epi.ldc * ELEM) % 16 == 0 && (reinterpret_cast<uintptr_t>(epi.C) & 15) == 0;
+  const bool tma_store = !epi_no_store<Epi>::value && ((size_t)epi.ldc * ELEM) % 16 == 0 && (reinterpret_cast<uintptr_t>(epi.C) & 15) == 0;
   if (tma_store) LLB_TRY(make_tensor_map_2d(&tmC, epi.C, ELEM, M, N, epi.ldc, Epi::CHUNK, 32, Epi::CHUNK * ELEM));
   else tmC = tmA;
   const int tiles = ceil_div(M, GEMM_BM) * ceil_div(N, BN);

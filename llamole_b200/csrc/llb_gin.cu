@@ -21,6 +21,8 @@ constexpr int BOND_VOCAB = 5;
 struct GinLayout {
   int H, L, predictor, out_dim, tdim, HH, HO;
   std::vector<size_t> mlp0_w, mlp4_w, vn0_w, vn4_w, adapter_w;   // bf16
+  std::vector<size_t> mlp_gram;                                    // bf16 (H,H): W0^T W0 of the bf16 node-MLP weight (analytic LayerNorm statistics)
+  std::vector<size_t> mlp_stat;                                    // fp32 [wbar (H) | 2 W0^T b (H) | bbar, |b|^2 / 4H, 0, 0]
   size_t head0_w, head4_w;
   size_t atom_emb, vn_emb, text_drop;                             // fp32
   std::vector<size_t> eps, mlp0_b, mlp_ln_w, mlp_ln_b, mlp4_b, bond_emb, norm_w, norm_b;
@@ -47,6 +49,7 @@ int make_layout(const llb_gin_config& c, GinLayout& G) {
   for (int l = 0; l < G.L; ++l) {
     G.mlp0_w.push_back(take(4 * H * H * 2));
     G.mlp4_w.push_back(take(4 * H * H * 2));
+    G.mlp_gram.push_back(take(H * H * 2));
     if (l < G.L - 1) {
       G.vn0_w.push_back(take(4 * H * H * 2));
       G.vn4_w.push_back(take(4 * H * H * 2));
@@ -62,6 +65,7 @@ int make_layout(const llb_gin_config& c, GinLayout& G) {
     G.eps.push_back(take(4));
     G.mlp0_b.push_back(take(4 * H * 4)), G.mlp_ln_w.push_back(take(4 * H * 4)), G.mlp_ln_b.push_back(take(4 * H * 4));
     G.mlp4_b.push_back(take(H * 4));
+    G.mlp_stat.push_back(take((2 * H + 4) * 4));
     G.bond_emb.push_back(take(BOND_VOCAB * H * 4));
     G.norm_w.push_back(take(H * 4)), G.norm_b.push_back(take(H * 4));
     if (l < G.L - 1) {
@@ -223,6 +227,121 @@ __global__ void __launch_bounds__(256) gin_aggregate_kernel(const float* __restr
         make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
   }
 }
+
+// ---------------------------------------------------------------------------------------------
+// Analytic LayerNorm statistics for the node MLP (Linear(H,4H) -> LayerNorm(4H) -> GELU -> Linear(4H,H), model.py:156-165).
+// The LayerNorm needs the mean and variance of a 4H-wide row z = W a + b that no single CTA holds, which is why the
+// unfused path writes z (757 MB per layer for 123 k nodes), re-reads and rewrites it in a row kernel and reads it again
+// in the second GEMM.  Both moments are functions of the H-wide INPUT row a:
+//     mean = a . wbar + bbar                                 wbar = column mean of W, bbar = mean of b
+//     E[z^2] = (a^T G a + 2 a . (W^T b) + |b|^2) / 4H        G = W^T W  (H x H, symmetric)
+// G, wbar, W^T b are computed once at pack time from the bf16-rounded W (what the tensor core multiplies by).  Per layer
+// one extra (n, H) x (H, H) GEMM -- a quarter of the first linear -- whose epilogue never stores its product: thread = row
+// takes the dot of its 32 accumulator columns (+ 2 W^T b / 4H) with the row's own a values, and a . wbar, into a
+// (n, H/32, 2) partial buffer; gin_ln_stats_kernel adds the partials in column order -> (mean, rstd) per row.  The first
+// linear's epilogue then applies LayerNorm + affine + GELU directly (EpiLnGelu), so z never exists un-normalised.
+// Numerics (tools/ln_analytic_study.py): against the two-pass LayerNorm the error of GELU(LN(z)) is 6e-4 max / 4e-5 rms
+// with G in bf16, 25x below the bf16 rounding of that output.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gin_gram_kernel(const __nv_bfloat16* __restrict__ W, int rows, int H, __nv_bfloat16* __restrict__ Gm) {
+  // Gm[i][j] = sum_o W[o][i] W[o][j]; one thread per (i, j), pack time only
+  const int j = blockIdx.x * 16 + (threadIdx.x & 15), i = blockIdx.y * 16 + (threadIdx.x >> 4);
+  if (i >= H || j >= H) return;
+  float acc = 0.f;
+  for (int o = 0; o < rows; ++o) acc = fmaf(__bfloat162float(W[(size_t)o * H + i]), __bfloat162float(W[(size_t)o * H + j]), acc);
+  Gm[(size_t)i * H + j] = __float2bfloat16(acc);
+}
+__global__ void __launch_bounds__(256) gin_stat_vectors_kernel(const __nv_bfloat16* __restrict__ W, const float* __restrict__ b, int rows, int H,
+                                                               float* __restrict__ out) {
+  // out = [wbar (H) | 2 W^T b (H) | bbar, |b|^2 / rows, 0, 0]
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < H) {
+    float sw = 0.f, sc = 0.f;
+    for (int o = 0; o < rows; ++o) {
+      const float w = __bfloat162float(W[(size_t)o * H + k]);
+      sw += w;
+      sc = fmaf(w, b[o], sc);
+    }
+    out[k] = sw / rows;
+    out[H + k] = 2.0f * sc;
+  }
+  if (k == 0) {
+    float sb = 0.f, sbb = 0.f;
+    for (int o = 0; o < rows; ++o) sb += b[o], sbb = fmaf(b[o], b[o], sbb);
+    out[2 * H] = sb / rows, out[2 * H + 1] = sbb / rows, out[2 * H + 2] = 0.f, out[2 * H + 3] = 0.f;
+  }
+}
+
+// Epilogue of the statistics GEMM S = a G: no matrix output.
+struct EpiRowStats {
+  static constexpr int CHUNK = 32;
+  static constexpr bool OUT_F32 = true;
+  static constexpr bool NO_STORE = true;
+  void* C;     // unused
+  int ldc;     // unused
+  const __nv_bfloat16* A;   // (M, lda) the GEMM's own A operand
+  int lda;
+  const float* stat;        // [wbar (N) | 2 W^T b (N) | ...]
+  float2* part;             // (M, N / 32) partial (a . (S + 2 W^T b), a . wbar) over 32 columns
+  __device__ __forceinline__ void transform(int row, int col0, float* v, int M, int N) const {
+    if (row >= M) return;
+    const uint4* ap = reinterpret_cast<const uint4*>(A + (size_t)row * lda + col0);
+    float q = 0.f, m = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint4 u = __ldg(ap + i);
+      const float a8[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y), bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(stat + col0 + 8 * i)), w1 = __ldg(reinterpret_cast<const float4*>(stat + col0 + 8 * i + 4));
+      const float4 c0 = __ldg(reinterpret_cast<const float4*>(stat + N + col0 + 8 * i)), c1 = __ldg(reinterpret_cast<const float4*>(stat + N + col0 + 8 * i + 4));
+      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      const float cv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        q = fmaf(a8[e], v[8 * i + e] + cv[e], q);   // a . (G a + 2 W^T b); the finaliser divides by the 4H rows of W
+        m = fmaf(a8[e], wv[e], m);                  // a . wbar
+      }
+    }
+    part[(size_t)row * (N / 32) + col0 / 32] = make_float2(q, m);
+  }
+};
+
+__global__ void __launch_bounds__(256) gin_ln_stats_kernel(const float2* __restrict__ part, int n, int chunks, const float* __restrict__ stat, int H,
+                                                           float inv_rows, float2* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float q = 0.f, m = 0.f;
+  for (int c = 0; c < chunks; ++c) {   // column order: deterministic
+    const float2 p = part[(size_t)i * chunks + c];
+    q += p.x, m += p.y;
+  }
+  const float mean = m + stat[2 * H];
+  const float ez2 = q * inv_rows + stat[2 * H + 1];
+  const float var = fmaxf(ez2 - mean * mean, 0.f);
+  out[i] = make_float2(mean, rsqrtf(var + 1e-5f));
+}
+
+// Epilogue of the first linear with the row statistics known: GELU(LayerNorm(acc + bias) * gamma + beta) -> bf16.
+struct EpiLnGelu {
+  static constexpr int CHUNK = 32;
+  static constexpr bool OUT_F32 = false;
+  void* C;
+  int ldc;
+  const float *bias, *gamma, *beta;   // (N)
+  const float2* stats;                // (M) mean, rstd
+  __device__ __forceinline__ void transform(int row, int col0, float* v, int M, int N) const {
+    const float2 st = row < M ? __ldg(stats + row) : make_float2(0.f, 1.f);
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col0 + i));
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + col0 + i));
+      const float4 t = __ldg(reinterpret_cast<const float4*>(beta + col0 + i));
+      v[i] = gelu_fast(fmaf((v[i] + b.x - st.x) * st.y, g.x, t.x));
+      v[i + 1] = gelu_fast(fmaf((v[i + 1] + b.y - st.x) * st.y, g.y, t.y));
+      v[i + 2] = gelu_fast(fmaf((v[i + 2] + b.z - st.x) * st.y, g.z, t.z));
+      v[i + 3] = gelu_fast(fmaf((v[i + 3] + b.w - st.x) * st.y, g.w, t.w));
+    }
+  }
+};
 
 // Per-graph pooling over the contiguous node range (graph_encoder/model.py:148,152): max -> bf16 operand of the
 // virtual-node MLP, sum -> fp32 (+bf16) read-out.  grid (B, ceil(H/256)).
@@ -598,6 +717,7 @@ struct llb_gin {
   __nv_bfloat16* agg = nullptr;
   __nv_bfloat16* z = nullptr;
   float* u = nullptr;
+  float2 *ln_part = nullptr, *ln_stats = nullptr;   // analytic LayerNorm statistics of the node MLP
   float *vn_cur = nullptr, *vn_next = nullptr, *vu = nullptr;
   __nv_bfloat16 *pool_b = nullptr, *vz = nullptr;
   float* mod = nullptr;
@@ -627,6 +747,7 @@ static int gin_carve(llb_gin* g, void* ws, size_t ws_bytes, int n, int e, int B,
   g->h = a.take<float>((size_t)n * H), g->hb = a.take<__nv_bfloat16>((size_t)n * H), g->agg = a.take<__nv_bfloat16>((size_t)n * H);
   g->z = a.take<__nv_bfloat16>((size_t)n * 4 * H);
   g->u = a.take<float>((size_t)n * H);
+  g->ln_part = a.take<float2>((size_t)n * (H / 32)), g->ln_stats = a.take<float2>((size_t)n);   // analytic LayerNorm statistics
   g->vn_cur = a.take<float>((size_t)B * H), g->vn_next = a.take<float>((size_t)B * H), g->vu = a.take<float>((size_t)B * H);
   g->pool_b = a.take<__nv_bfloat16>((size_t)B * H), g->vz = a.take<__nv_bfloat16>((size_t)B * 4 * H);
   if (G.predictor) {
@@ -672,9 +793,28 @@ static int gin_scan(llb_gin* g, cudaStream_t s) {
 
 static int gin_mlp4(llb_gin* g, const __nv_bfloat16* in, int rows, size_t w0, size_t b0, size_t lnw, size_t lnb, size_t w4, size_t b4,
                     int hidden, int out_f, __nv_bfloat16* zbuf, float* out, int out_ld, cudaStream_t s, int slot0 = LLB_PROF_GIN_MISC,
-                    int slot4 = LLB_PROF_GIN_MISC) {
+                    int slot4 = LLB_PROF_GIN_MISC, int gram_layer = -1) {
   // Linear -> LayerNorm(hidden) -> GELU -> Linear  (the 4H MLP of GINConv / virtual node / heads)
   const int H = g->G.H;
+  if (gram_layer >= 0) {
+    // node MLP with analytic LayerNorm statistics: statistics GEMM (no output matrix) -> per-row (mean, rstd) -> first linear
+    // with LayerNorm + GELU in its epilogue -> second linear.  The un-normalised 4H-wide intermediate never exists.
+    const GinLayout& G = g->G;
+    g->ctr.slot = slot0;
+    EpiRowStats es{nullptr, 0, in, H, g->w<float>(G.mlp_stat[gram_layer]), g->ln_part};
+    LLB_TRY((launch_gemm<256>(in, H, g->w<void>(G.mlp_gram[gram_layer]), H, rows, H, H, es, s, &g->ctr)));
+    {
+      ProfScope prof(LLB_PROF_GIN_ROWLN, s);
+      gin_ln_stats_kernel<<<ceil_div(rows, 256), 256, 0, s>>>(g->ln_part, rows, H / 32, g->w<float>(G.mlp_stat[gram_layer]), H, 1.0f / (float)hidden,
+                                                              g->ln_stats);
+    }
+    LLB_CUDA_OK(cudaGetLastError());
+    g->launches++;
+    EpiLnGelu el{zbuf, hidden, g->w<float>(b0), g->w<float>(lnw), g->w<float>(lnb), g->ln_stats};
+    LLB_TRY((launch_gemm<256>(in, H, g->w<void>(w0), H, rows, hidden, H, el, s, &g->ctr)));
+    g->ctr.slot = slot4;
+    return gemm_bias_act(zbuf, hidden, g->w<void>(w4), hidden, g->w<float>(b4), out, out_ld, rows, out_f, hidden, LLB_ACT_NONE, true, s, &g->ctr);
+  }
   g->ctr.slot = slot0;
   LLB_TRY(gemm_bias_act(in, H, g->w<void>(w0), H, g->w<float>(b0), zbuf, hidden, rows, hidden, H, LLB_ACT_NONE, false, s, &g->ctr));
   RowLnArgs a;
@@ -734,8 +874,13 @@ static int gin_trunk(llb_gin* g, const float* c, cudaStream_t s) {
       LLB_TRY(launch_row_ln(a, s));
       g->launches++;
     }
+    // LLB_GIN_ANALYTIC_LN=1: LayerNorm + GELU in the first linear's epilogue from analytic row statistics (see EpiRowStats).
+    // Parity-green on B200 (all GIN tests; encoder embedding max |d| 2.0e-3 vs 2.8e-3 unfused) but only 1.6 % faster so far
+    // (8.70 vs 8.84 ms: row kernels -1.36 ms, statistics GEMM + heavier epilogue +1.17 ms), hence still opt-in: the
+    // statistics epilogue re-reads its A rows from L2 with 16-byte row-strided loads and is epilogue-bound at K = H.
+    static const bool analytic_ln = getenv("LLB_GIN_ANALYTIC_LN") && getenv("LLB_GIN_ANALYTIC_LN")[0] == '1';
     LLB_TRY(gin_mlp4(g, g->agg, n, G.mlp0_w[l], G.mlp0_b[l], G.mlp_ln_w[l], G.mlp_ln_b[l], G.mlp4_w[l], G.mlp4_b[l], 4 * H, H, g->z,
-                     g->u, H, s, LLB_PROF_GIN_GEMM_MLP0, LLB_PROF_GIN_GEMM_MLP4));
+                     g->u, H, s, LLB_PROF_GIN_GEMM_MLP0, LLB_PROF_GIN_GEMM_MLP4, (analytic_ln && H % 32 == 0) ? l : -1));
     RowLnArgs a;
     a.in = g->u, a.in_ld = H, a.rows = n, a.width = H;
     a.row_group = g->batch32;
@@ -797,6 +942,10 @@ int llb_gin_pack_weights(const llb_gin_config* cfg, const llb_gin_weights* w, vo
     LLB_CUDA_OK(cp(G.mlp_ln_w[l], w->mlp_ln_w[l], 4 * H));
     LLB_CUDA_OK(cp(G.mlp_ln_b[l], w->mlp_ln_b[l], 4 * H));
     LLB_CUDA_OK(cp(G.mlp4_b[l], w->mlp4_b[l], H));
+    // analytic LayerNorm statistics of the node MLP: from the bf16-rounded weight the tensor core multiplies by
+    gin_gram_kernel<<<dim3(ceil_div(H, 16), ceil_div(H, 16)), 256, 0, s>>>(bf(G.mlp0_w[l]), 4 * H, H, bf(G.mlp_gram[l]));
+    gin_stat_vectors_kernel<<<ceil_div(H, 256), 256, 0, s>>>(bf(G.mlp0_w[l]), w->mlp0_b[l], 4 * H, H, reinterpret_cast<float*>(base + G.mlp_stat[l]));
+    LLB_CUDA_OK(cudaGetLastError());
     LLB_CUDA_OK(cp(G.bond_emb[l], w->bond_emb[l], (size_t)BOND_VOCAB * H));
     if (!G.predictor) {
       LLB_CHECK_ARG(w->norm_w && w->norm_b, "gin: the encoder needs norms.{l}.weight/bias");
