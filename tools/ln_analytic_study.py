@@ -53,3 +53,9 @@ def var_c(Gm): return ((A@Gm)*A).sum(1)/N + 2*(A@cc)/N + (b1c*b1c).sum()/N
 report("centred fp32 Gc", mu_a, var_c(Gc))
 report("centred bf16 Gc", mu_a, var_c(bf(Gc)))
 print("z std per row (median)", float(var.sqrt().median()), "mean |mu|", float(mu.abs().mean()))
+
+# ---- variant without any A reads in the statistics epilogue: G = R^T R (Cholesky, fp64 at pack time), q = |R a|^2
+Gd = (W1.double().t() @ W1.double())
+Rm = torch.linalg.cholesky(Gd + 1e-9 * torch.eye(H, dtype=torch.float64) * float(Gd.diagonal().mean()), upper=True).float()   # G = R^T R
+Y = A @ bf(Rm).t()                      # what the statistics GEMM would hold in its accumulators (bf16 R, fp32 accumulate)
+report("bf16 Cholesky factor, q = sum_k Y_k^2", mu_a, (Y * Y).sum(1) / N + 2 * (A @ c) / N + (b1 * b1).sum() / N - mu_a ** 2)
