@@ -28,9 +28,13 @@ def balanced_graph_ranges(nodes_per_graph: Sequence[int], world: int) -> List[Tu
     prefix = torch.cumsum(counts, 0)
     total = int(prefix[-1]) if G else 0
     bounds = [0]
+    pf = prefix.double()
     for r in range(1, world):
         target = total * r / world
-        cut = int(torch.searchsorted(prefix, torch.tensor(target, dtype=prefix.dtype)).item())
+        cut = int(torch.searchsorted(pf, torch.tensor(target, dtype=torch.float64), right=True).item())   # graphs with prefix <= target
+        # the boundary whose node prefix is nearest to the target: after `cut` graphs or after one more
+        if cut < G and (cut == 0 or float(pf[cut]) - target < target - float(pf[cut - 1])):
+            cut += 1
         bounds.append(min(max(cut, bounds[-1]), G))
     bounds.append(G)
     return [(bounds[i], bounds[i + 1]) for i in range(world)]
