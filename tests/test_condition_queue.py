@@ -206,3 +206,36 @@ def test_queue_sharded_world2():
     assert [g[0] for g in got] == [0, 1]
     assert all(g[1] for g in got)
     assert all(g[2] <= 3 for g in got)      # chunks of 5 molecules are split over the two ranks
+
+
+# ------------------------------------------------------------------------------------------------ property test
+from hypothesis import given, settings  # noqa: E402
+from hypothesis import strategies as st  # noqa: E402
+
+
+@settings(max_examples=60, deadline=None)
+@given(sizes=st.lists(st.integers(0, 9), min_size=1, max_size=8), max_batch=st.integers(1, 12),
+       flush_after=st.lists(st.booleans(), min_size=8, max_size=8), seed=st.integers(0, 50))
+def test_queue_any_interleaving_of_submit_and_flush(sizes, max_batch, flush_after, seed):
+    """Whatever the request sizes, chunk size and flush points, every request gets exactly what a direct call with its
+    own global index base and node counts returns, and no sampler call exceeds max_batch."""
+    reqs = _requests(sizes, seed=seed)
+    m = _FakeDit()
+    q = ConditionQueue(m, max_batch=max_batch, seed=seed)
+    tickets = []
+    for i, (p, t) in enumerate(reqs):
+        tickets.append(q.submit(p, t))
+        if flush_after[i]:
+            q.flush()
+    base = 0
+    for (p, t), tk in zip(reqs, tickets):
+        assert tk.start == base and tk.count == p.shape[0]
+        base += p.shape[0]
+        X, E, n = q.result(tk)
+        assert X.shape[0] == tk.count
+        if tk.count:
+            Xd, Ed, _ = _FakeDit().generate_graphs(torch.where(p == -200.0, float("nan"), p), t, n_nodes=n, seed=seed, mol_index_base=tk.start)
+            assert torch.equal(X, Xd) and torch.equal(E, Ed)
+            assert torch.equal(n, ConditionQueue(_FakeDit(), seed=seed)._draw_n_nodes(tk.start, tk.count))
+    assert q.pending() == 0
+    assert all(b <= max_batch for b, _ in m.calls) and sum(b for b, _ in m.calls) == sum(sizes)
