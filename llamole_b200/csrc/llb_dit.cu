@@ -306,7 +306,10 @@ static int dit_forward(llb_dit* h, int t, cudaStream_t s) {
   // its 6H x H weight is rows [l 6H, (l+1) 6H) of the stacked operand); mod is (B+1, D, 6H).  LLB_ADALN_GROUPED=0: D launches.
   static const bool adaln_split = getenv("LLB_ADALN_GROUPED") && getenv("LLB_ADALN_GROUPED")[0] == '0';
   const int ldm = D * 6 * H;
-  if (!adaln_split && (6 * H) % 256 == 0) {
+  // the stacked operand needs the D weights (and biases) back to back in the blob: true whenever 6 H H 2 and 6 H 4 bytes are
+  // multiples of the blob's 256-byte alignment; checked rather than assumed
+  const bool stacked = D == 1 || (L.ada2_w[1] - L.ada2_w[0] == (size_t)6 * H * H * 2 && L.ada2_b[1] - L.ada2_b[0] == (size_t)6 * H * 4);
+  if (!adaln_split && stacked && (6 * H) % 256 == 0) {
     GemmGroups grp;
     grp.group_n = 6 * H, grp.group_k = H;
     LLB_TRY(gemm_bias_act(h->hid, ldh, h->w<void>(L.ada2_w[0]), H, h->w<float>(L.ada2_b[0]), h->mod, ldm, B + 1, ldm, H, LLB_ACT_SOFTSIGN, true, s,
