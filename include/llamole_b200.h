@@ -57,6 +57,18 @@ enum {
 int llb_profile_enable(int on);
 int llb_profile_read(int slot, double* total_ms, int64_t* launches);
 const char* llb_profile_slot_name(int slot);
+/* Launch counters per kernel FAMILY since the library was loaded (process-wide).  The parity tests use them to assert that
+ * a shape really reached the kernel it is meant to cover (e.g. the CTA-pair GEMM, which only runs on wide problems). */
+enum {
+  LLB_KERN_GEMM_1CTA = 0,    /* gemm_tcgen05_kernel */
+  LLB_KERN_GEMM_2CTA,        /* gemm_tcgen05_2cta_kernel (cta_group::2) */
+  LLB_KERN_GEMM_LN_PAIR,     /* gemm_ln_pair_kernel */
+  LLB_KERN_GEMM_LN_CLUSTER,  /* gemm_ln_cluster_kernel */
+  LLB_KERN_GIN_FUSED_MLP,    /* gin_mlp_fused_kernel (aggregation-fed GEMM chain of a GIN layer) */
+  LLB_KERN_HEAD_TOPK,        /* gemm_head_topk_kernel (predictor head GEMM + online softmax + top-k) */
+  LLB_KERN_FAMILIES
+};
+int64_t llb_kernel_launches(int family);
 
 /* ------------------------------------------------------------------------------------------------------
  * tcgen05 GEMM building block:  C[M,N] = act(A[M,K] . W[N,K]^T + bias[N])
@@ -254,6 +266,16 @@ int llb_gin_workspace_bytes(const llb_gin_config* cfg, int num_nodes, int num_ed
 int llb_gin_bind(llb_gin* h, void* workspace, size_t workspace_bytes, int num_nodes, int num_edges, int num_graphs,
                  const int64_t* x, const int64_t* edge_index, const int64_t* edge_attr, const int64_t* batch,
                  llb_stream_t stream);
+/* Input defects of the batch bound last, as a bit mask written to *flags_host (the one call of this header that SYNCHRONISES
+ * the stream: it is how the Python classes raise the IndexError the reference raises for such inputs, graph_encoder/model.py:125,
+ * :169).  The kernels themselves clamp / skip the offending entries and never index out of bounds. */
+enum {
+  LLB_GIN_BAD_ATOM_ID = 1,  /* x outside [0,118) */
+  LLB_GIN_BAD_BATCH = 2,    /* batch not ascending or outside [0,num_graphs) */
+  LLB_GIN_BAD_EDGE = 4,     /* edge endpoint outside [0,num_nodes) */
+  LLB_GIN_BAD_BOND_ID = 8   /* edge_attr outside [0,5) */
+};
+int llb_gin_input_flags(llb_gin* h, int32_t* flags_host, llb_stream_t stream);
 /* GraphCLIP.forward: unit-norm embeddings (B,H) fp32. */
 int llb_gin_encoder_forward(llb_gin* h, float* out, float* pooled_or_null, llb_stream_t stream);
 /* GNNRetrosynthsizer.forward: logits (B,out_dim) fp32.  c (B,text_dim) fp32 or NULL (= text_dropping row). */

@@ -67,6 +67,7 @@ SIGNATURES = {
     "llb_profile_enable": (_I, [_I]),
     "llb_profile_read": (_I, [_I, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "llb_profile_slot_name": (C.c_char_p, [_I]),
+    "llb_kernel_launches": (C.c_int64, [_I]),
     "llb_gemm_bf16": (_I, [_P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "llb_gemm_ln_residual": (_I, [_P, _I, _P, _I, _P, _P, _P, _P, _P, _I, _P, _I, _P, _I, _I, _I, _I, _P]),
     "llb_gemm_ln_workspace_bytes": (_I, [C.POINTER(_SZ)]),
@@ -91,6 +92,7 @@ SIGNATURES = {
     "llb_gin_destroy": (None, [_P]),
     "llb_gin_workspace_bytes": (_I, [C.POINTER(GinConfig), _I, _I, _I, _I, C.POINTER(_SZ)]),
     "llb_gin_bind": (_I, [_P, _P, _SZ, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "llb_gin_input_flags": (_I, [_P, C.POINTER(C.c_int32), _P]),
     "llb_gin_encoder_forward": (_I, [_P, _P, _P, _P]),
     "llb_gin_predictor_forward": (_I, [_P, _P, _P, _P]),
     "llb_gin_predictor_topk": (_I, [_P, _P, _I, _P, _P, _P]),
@@ -148,9 +150,23 @@ def stream_ptr() -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def params_fingerprint(module) -> tuple:
+    """Identity + version of every parameter of `module`: changes when a parameter is replaced, moved, cast or written in
+    place (torch bumps `_version` on every in-place write), which is when a packed-weight blob made from it is stale."""
+    return tuple((p.data_ptr(), p._version, p.dtype) for p in module.parameters())
+
+
 def require_cuda(t, name: str):
     if not t.is_cuda:
         raise LlamoleB200Error(f"{name} must live on a CUDA (sm_100) device; llamole_b200 has no CPU path")
+
+
+KERN_GEMM_1CTA, KERN_GEMM_2CTA, KERN_GEMM_LN_PAIR, KERN_GEMM_LN_CLUSTER, KERN_GIN_FUSED_MLP, KERN_HEAD_TOPK = range(6)
+
+
+def kernel_launches(family: int) -> int:
+    """Launches of a kernel family since the library was loaded (include/llamole_b200.h: LLB_KERN_*)."""
+    return int(lib().llb_kernel_launches(int(family)))
 
 
 PROF_SLOTS = 18

@@ -103,7 +103,6 @@ class ConditionQueue:
         n_nodes = torch.cat([p[3] for p in self._pending])
         # global index of every pending molecule (tickets need not be contiguous after partial flushes)
         gidx = torch.cat([torch.arange(t.start, t.start + t.count) for t in tickets])
-        self._pending = []
         total = int(props.shape[0])
         Xs, Es, ns = [], [], []
         pos = 0
@@ -119,13 +118,16 @@ class ConditionQueue:
             def gen(p, t, n_nodes, seed, mol_index_base, _base=base, **k):
                 return self._gen(p, t, float("nan"), n_nodes=n_nodes, seed=seed, mol_index_base=_base + mol_index_base, **k)
 
+            # a failure here (out of memory, a collective error) propagates with the queue untouched: `_pending` is only
+            # cleared once every chunk has been sampled, so the caller can retry flush() and no ticket is lost
             X, E, n = sharding.sample_graphs_sharded(gen, props[pos:end], txt[pos:end], n_nodes[pos:end], seed=self.seed,
-                                                     group=self.group, **kw)
+                                                     group=self.group, max_nodes=int(self.model.max_n_nodes), **kw)
             Xs.append(X.cpu())
             Es.append(E.cpu())
             ns.append(n.cpu())
             pos = end
         X, E, n = torch.cat(Xs), torch.cat(Es), torch.cat(ns)
+        self._pending = [p for p in self._pending if p[0] not in set(tickets)]
         pos = 0
         for t in tickets:
             self._done[t] = (X[pos:pos + t.count], E[pos:pos + t.count], n[pos:pos + t.count])

@@ -55,6 +55,8 @@ struct ProfScope {
   }
 };
 
+void note_kernel(int family);   // llb_kernel_launches counters
+
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

@@ -575,6 +575,7 @@ int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, in
       const int pairs = pair_tiles < num_sms() / 2 ? pair_tiles : num_sms() / 2;
       ProfScope prof(ctr ? ctr->slot : LLB_PROF_GEMM_OTHER, stream);
       kern<<<2 * pairs, GEMM_THREADS, Gemm2Cfg::SMEM_BYTES, stream>>>(tmA, tmBh, tmC, M, N, K, epi, grp.group_n, grp.group_k, grp.split_k ? 1 : 0);
+      note_kernel(LLB_KERN_GEMM_2CTA);
       return LLB_OK;
     };
     if (tma_store) LLB_TRY(launch2(gemm_tcgen05_2cta_kernel<true, Epi>, 2));
@@ -587,6 +588,7 @@ int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, in
       }
       ProfScope prof(ctr ? ctr->slot : LLB_PROF_GEMM_OTHER, stream);
       kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, M, N, K, epi, grp.group_n, grp.group_k, grp.split_k ? 1 : 0);
+      note_kernel(LLB_KERN_GEMM_1CTA);
       return LLB_OK;
     };
     if (tma_store) LLB_TRY(launch(gemm_tcgen05_kernel<BN, true, Epi>, 0));

@@ -1023,6 +1023,7 @@ int launch_gemm_ln(const void* A, int lda, const void* W, int ldw, int M, int N,
   {
     ProfScope prof(ctr ? ctr->slot : LLB_PROF_GEMM_OTHER, stream);
     LLB_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_ln_cluster_kernel, tmA, tmB, tmX, tmXb, tmXpf, M, K, CL, e));
+    note_kernel(LLB_KERN_GEMM_LN_CLUSTER);
   }
   LLB_CUDA_OK(cudaGetLastError());
   if (ctr) ctr->launches++;
@@ -1105,6 +1106,7 @@ int launch_gemm_ln_pair(const void* A, int lda, const void* W, int ldw, int M, i
       err = cudaLaunchKernelEx(&cfg, kern, tmA, tmBh, tmX, tmXb, tmXpf, M, K, G, e, stats, tag_base, prefetch_x);
     }
     LLB_CUDA_OK(err);
+    note_kernel(LLB_KERN_GEMM_LN_PAIR);
   }
   LLB_CUDA_OK(cudaGetLastError());
   if (ctr) ctr->launches++;

@@ -83,25 +83,36 @@ int make_layout(const llb_gin_config& c, GinLayout& G) {
 // ---------------------------------------------------------------------------------------------
 // Graph preparation
 // ---------------------------------------------------------------------------------------------
+// Input defects are recorded in a flag word (llb_gin_input_flags) and made harmless here: ids are clamped, a graph id outside
+// [0, B) or a descending `batch` never indexes outside graph_ptr[0..B].  The reference raises an index error for the same inputs
+// (nn.Embedding / scatter); the Python classes turn a non-zero flag word into that error.
 __global__ void gin_prep_nodes_kernel(const int64_t* __restrict__ x, const int64_t* __restrict__ batch, int32_t* __restrict__ x32,
-                                      int32_t* __restrict__ batch32, int32_t* __restrict__ graph_ptr, int n, int B) {
+                                      int32_t* __restrict__ batch32, int32_t* __restrict__ graph_ptr, int32_t* __restrict__ flags, int n,
+                                      int B) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  int xv = (int)x[i];
-  x32[i] = xv < 0 ? 0 : (xv >= ATOM_VOCAB ? ATOM_VOCAB - 1 : xv);
-  const int g = (int)batch[i];
+  const long long xv = x[i];
+  if (xv < 0 || xv >= ATOM_VOCAB) atomicOr(flags, LLB_GIN_BAD_ATOM_ID);
+  x32[i] = xv < 0 ? 0 : (xv >= ATOM_VOCAB ? ATOM_VOCAB - 1 : (int)xv);
+  const long long gl = batch[i];
+  const long long pl = i == 0 ? -1 : batch[i - 1];
+  if (gl < 0 || gl >= B || gl < pl) atomicOr(flags, LLB_GIN_BAD_BATCH);
+  const int g = gl < 0 ? 0 : (gl >= B ? B - 1 : (int)gl);
+  const int prev = pl < -1 ? -1 : (pl >= B ? B - 1 : (int)pl);
   batch32[i] = g;
-  const int prev = i == 0 ? -1 : (int)batch[i - 1];
-  for (int k = prev + 1; k <= g; ++k) graph_ptr[k] = i;   // first node of graph k (empty graphs collapse onto i)
+  for (int k = prev + 1; k <= g; ++k) graph_ptr[k] = i;   // first node of graph k (empty graphs collapse onto i); k <= g < B
   if (i == n - 1)
     for (int k = g + 1; k <= B; ++k) graph_ptr[k] = n;
 }
 
-__global__ void gin_degree_kernel(const int64_t* __restrict__ edge_index, int32_t* __restrict__ deg, int e, int n) {
+__global__ void gin_degree_kernel(const int64_t* __restrict__ edge_index, const int64_t* __restrict__ edge_attr, int32_t* __restrict__ deg,
+                                  int32_t* __restrict__ flags, int e, int n) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= e) return;
-  const int dst = (int)edge_index[(size_t)e + k];
-  if (dst >= 0 && dst < n) atomicAdd(&deg[dst], 1);
+  const long long src = edge_index[k], dst = edge_index[(size_t)e + k], a = edge_attr[k];
+  if (src < 0 || src >= n || dst < 0 || dst >= n) atomicOr(flags, LLB_GIN_BAD_EDGE);
+  if (a < 0 || a >= BOND_VOCAB) atomicOr(flags, LLB_GIN_BAD_BOND_ID);
+  if (dst >= 0 && dst < n) atomicAdd(&deg[(int)dst], 1);
 }
 
 // Exclusive scan in three phases (block sums of 1024 elements).
@@ -143,13 +154,13 @@ __global__ void gin_fill_kernel(const int64_t* __restrict__ edge_index, const in
                                 int32_t* __restrict__ eid, int e, int n) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= e) return;
-  const int src = (int)edge_index[k];
-  const int dst = (int)edge_index[(size_t)e + k];
-  if (dst < 0 || dst >= n) return;
+  const long long srcl = edge_index[k], dstl = edge_index[(size_t)e + k];
+  if (dstl < 0 || dstl >= n) return;
+  const int dst = (int)dstl;
   const int pos = rowptr[dst] + atomicAdd(&cursor[dst], 1);
-  int a = (int)edge_attr[k];
-  a = a < 0 ? 0 : (a >= BOND_VOCAB ? BOND_VOCAB - 1 : a);
-  col[pos] = (src < 0 || src >= n) ? dst : src;
+  const long long al = edge_attr[k];
+  const int a = al < 0 ? 0 : (al >= BOND_VOCAB ? BOND_VOCAB - 1 : (int)al);
+  col[pos] = (srcl < 0 || srcl >= n) ? dst : (int)srcl;
   eid[pos] = (k << 3) | a;   // edge id (deterministic order key) with the bond type in the low bits
 }
 // Sort every row by original edge id so that the floating-point summation order is run-to-run deterministic.
@@ -712,6 +723,7 @@ struct llb_gin {
   bool want_logits = false;
   int32_t *x32 = nullptr, *batch32 = nullptr, *graph_ptr = nullptr, *rowptr = nullptr, *col = nullptr, *eid = nullptr;
   int32_t *deg = nullptr, *blk = nullptr, *blk2 = nullptr;
+  int32_t* flags = nullptr;   // input-defect bits of the bound batch (LLB_GIN_BAD_*)
   float* h = nullptr;
   __nv_bfloat16* hb = nullptr;
   __nv_bfloat16* agg = nullptr;
@@ -742,6 +754,7 @@ static int gin_carve(llb_gin* g, void* ws, size_t ws_bytes, int n, int e, int B,
   g->x32 = a.take<int32_t>(n), g->batch32 = a.take<int32_t>(n), g->graph_ptr = a.take<int32_t>(B + 1);
   g->rowptr = a.take<int32_t>(n + 1), g->col = a.take<int32_t>(e > 0 ? e : 1), g->eid = a.take<int32_t>(e > 0 ? e : 1);
   g->deg = a.take<int32_t>(n + 1);
+  g->flags = a.take<int32_t>(4);
   const int nb = ceil_div(n + 1, 1024);
   g->blk = a.take<int32_t>(nb + 1), g->blk2 = a.take<int32_t>(ceil_div(nb, 1024) + 1);
   g->h = a.take<float>((size_t)n * H), g->hb = a.take<__nv_bfloat16>((size_t)n * H), g->agg = a.take<__nv_bfloat16>((size_t)n * H);
@@ -1021,11 +1034,12 @@ int llb_gin_bind(llb_gin* g, void* workspace, size_t workspace_bytes, int num_no
   }
   g->n = num_nodes, g->e = num_edges, g->B = num_graphs;
   const int n = num_nodes, e = num_edges;
-  gin_prep_nodes_kernel<<<ceil_div(n, 256), 256, 0, s>>>(x, batch, g->x32, g->batch32, g->graph_ptr, n, num_graphs);
+  LLB_CUDA_OK(cudaMemsetAsync(g->flags, 0, 16, s));
+  gin_prep_nodes_kernel<<<ceil_div(n, 256), 256, 0, s>>>(x, batch, g->x32, g->batch32, g->graph_ptr, g->flags, n, num_graphs);
   LLB_CUDA_OK(cudaGetLastError());
   LLB_CUDA_OK(cudaMemsetAsync(g->deg, 0, (size_t)(n + 1) * 4, s));
   if (e > 0) {
-    gin_degree_kernel<<<ceil_div(e, 256), 256, 0, s>>>(edge_index, g->deg, e, n);
+    gin_degree_kernel<<<ceil_div(e, 256), 256, 0, s>>>(edge_index, edge_attr, g->deg, g->flags, e, n);
     LLB_CUDA_OK(cudaGetLastError());
   }
   LLB_TRY(gin_scan(g, s));
@@ -1036,6 +1050,14 @@ int llb_gin_bind(llb_gin* g, void* workspace, size_t workspace_bytes, int num_no
     LLB_CUDA_OK(cudaGetLastError());
   }
   g->launches += 4;
+  return LLB_OK;
+}
+
+int llb_gin_input_flags(llb_gin* g, int32_t* flags_host, llb_stream_t stream) {
+  LLB_CHECK_ARG(g && flags_host && g->flags, "llb_gin_input_flags: no graph batch bound");
+  cudaStream_t s = (cudaStream_t)stream;
+  LLB_CUDA_OK(cudaMemcpyAsync(flags_host, g->flags, 4, cudaMemcpyDeviceToHost, s));
+  LLB_CUDA_OK(cudaStreamSynchronize(s));
   return LLB_OK;
 }
 

@@ -24,6 +24,11 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+static int64_t g_kernel_launches[LLB_KERN_FAMILIES];
+void note_kernel(int family) {
+  if (family >= 0 && family < LLB_KERN_FAMILIES) __atomic_add_fetch(&g_kernel_launches[family], 1, __ATOMIC_RELAXED);
+}
+
 // ---- live profiling -------------------------------------------------------------------------------
 namespace {
 struct ProfRec {
@@ -252,6 +257,10 @@ const char* llb_profile_slot_name(int slot) {
       "dit_misc", "gin_aggregate", "gin_pool", "gin_gemm_mlp0", "gin_gemm_mlp4", "gin_rowln", "gin_misc", "gin_gemm_head",
       "gin_topk"};
   return (slot >= 0 && slot < LLB_PROF_SLOTS) ? names[slot] : "?";
+}
+
+int64_t llb_kernel_launches(int family) {
+  return (family >= 0 && family < LLB_KERN_FAMILIES) ? __atomic_load_n(&llb::g_kernel_launches[family], __ATOMIC_RELAXED) : -1;
 }
 
 int llb_arch_check(int device) {

@@ -101,7 +101,11 @@ class GinEngine:
         except Exception:
             pass
 
-    def bind(self, x, edge_index, edge_attr, batch, num_graphs: Optional[int] = None, want_logits: bool = False):
+    def bind(self, x, edge_index, edge_attr, batch, num_graphs: Optional[int] = None, want_logits: bool = False,
+             validate: bool = True):
+        """Binds a PyG-layout batch (builds the CSR on the device).  `validate` reads the kernels' input-defect flags back
+        (one stream synchronisation, like the reference's own host read of batch[-1]) and raises the IndexError the
+        reference's nn.Embedding / scatter raise for ids or indices out of range; pass False inside device-timed loops."""
         dev = self.device
         x = x.to(dev, torch.int64).contiguous()
         edge_index = edge_index.to(dev, torch.int64).contiguous()
@@ -123,6 +127,14 @@ class GinEngine:
             _cabi.check(self.lib.llb_gin_bind(self.handle, _cabi.ptr(self.workspace), need.value, n, e, B, _cabi.ptr(x),
                                               _cabi.ptr(edge_index), _cabi.ptr(edge_attr), _cabi.ptr(batch), _cabi.stream_ptr()),
                         "llb_gin_bind")
+            if validate:
+                flags = C.c_int32(0)
+                _cabi.check(self.lib.llb_gin_input_flags(self.handle, C.byref(flags), _cabi.stream_ptr()), "llb_gin_input_flags")
+                if flags.value:
+                    names = ((1, "atom id outside [0,118)"), (2, "`batch` not ascending or outside [0,num_graphs)"),
+                             (4, "edge endpoint outside [0,num_nodes)"), (8, "bond type outside [0,5)"))
+                    what = [msg for bit, msg in names if flags.value & bit]
+                    raise IndexError("index out of range in the graph batch: " + "; ".join(what))
         self.B = B
         return B
 

@@ -198,9 +198,15 @@ class GraphDiT(nn.Module):
         return next(self.denoiser.parameters()).device
 
     def engine(self) -> "_DitEngine":
+        """The packed-weight engine of the current parameters.  It is rebuilt whenever a parameter was replaced, moved or
+        written in place since it was packed (`load_state_dict`, the reference loader's `param.data = param.data.to(dtype)`
+        cast loop, `.to(device)`, fine-tuning steps): the fingerprint below is every parameter's (data_ptr, _version)."""
         dev = self._device()
-        if self._engine is None or self._engine.device != dev:
+        fp = _cabi.params_fingerprint(self.denoiser)
+        if self._engine is None or self._engine.device != dev or self._engine.fingerprint != fp:
+            self._engine = None   # release the old blob first
             self._engine = _DitEngine(self, dev)
+            self._engine.fingerprint = fp
         return self._engine
 
     def sample_n_nodes(self, batch_size: int, generator: Optional[torch.Generator] = None) -> torch.Tensor:
@@ -208,7 +214,7 @@ class GraphDiT(nn.Module):
         return torch.multinomial(self.node_prob, batch_size, replacement=True, generator=generator)
 
     @torch.no_grad()
-    def generate_graphs(self, properties, text_embedding, no_label_index=-200, n_nodes=None, noise=None, seed=0,
+    def generate_graphs(self, properties, text_embedding, no_label_index=-200, n_nodes=None, noise=None, seed: Optional[int] = None,
                         steps: Optional[int] = None, mol_index_base: int = 0):
         """The timed region of `generate`: conditions -> integer graphs.
 
@@ -216,10 +222,20 @@ class GraphDiT(nn.Module):
         `noise` = dict(qX0,qE0,qX,qE) of pre-drawn Exp(1) tensors reproduces the reference bit for bit given the
         same tensors (oracle parity); otherwise the in-kernel counter RNG keyed by (seed, step, molecule, position).
         `steps` truncates the loop to the first `steps` reverse steps (benchmark sampling only).
+        `seed=None` (what `generate` uses) draws a fresh 62-bit seed from torch's global generator on every call, like the
+        reference, whose multinomial draws advance the global generator (diffusion_utils.py:376-413): repeated calls with the
+        same conditions give different molecules, and `torch.manual_seed` makes a run reproducible.  An explicit seed keys
+        the counter RNG by (seed, step, mol_index_base + row, position) and reproduces the same graphs on every call.
         """
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (), dtype=torch.int64).item())
         eng = self.engine()
         dev = eng.device
         B = properties.shape[0]
+        if B == 0:   # an empty shard of a sharded batch (sharding.sample_graphs_sharded): nothing to sample
+            N = self.max_n_nodes
+            z = lambda *shape: torch.zeros(shape, dtype=torch.int64, device=dev)  # noqa: E731
+            return z(0, N), z(0, N, N), z(0)
         if n_nodes is None:
             n_nodes = self.sample_n_nodes(B)
         n_host = n_nodes.to("cpu", torch.int32).contiguous()

@@ -9,6 +9,7 @@ import os
 import torch
 import torch.nn as nn
 
+from . import _cabi
 from .gin_engine import GinEngine, _Holder, gin_trunk_skeleton
 
 
@@ -53,13 +54,16 @@ class GraphCLIP(nn.Module):
 
     def engine(self) -> GinEngine:
         dev = next(self.parameters()).device
-        if self._engine is None or self._engine.device != dev:
+        fp = _cabi.params_fingerprint(self)   # repack when a parameter was replaced / cast / written in place
+        if self._engine is None or self._engine.device != dev or self._engine.fingerprint != fp:
+            self._engine = None
             f32 = lambda sd: {k: v.detach().to(dev, torch.float32).contiguous() for k, v in sd.items()}  # noqa: E731
             trunk = f32(self.molecule_encoder.state_dict())
             pj = f32(self.molecule_projection.state_dict())
             head = {"w0": pj["fc1.weight"], "b0": pj["fc1.bias"], "lnw": pj["norm1.weight"], "lnb": pj["norm1.bias"],
                     "w4": pj["fc2.weight"], "b4": pj["fc2.bias"]}
             self._engine = GinEngine(dev, self.hidden_size, self.num_layer, False, 0, 0, trunk, head)
+            self._engine.fingerprint = fp
         return self._engine
 
     @torch.no_grad()

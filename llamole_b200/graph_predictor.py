@@ -99,11 +99,14 @@ class GraphPredictor(nn.Module):
     # ------------------------------------------------------------------ device path
     def engine(self) -> GinEngine:
         dev = next(self.predictor.parameters()).device
-        if self._engine is None or self._engine.device != dev:
+        fp = _cabi.params_fingerprint(self.predictor)   # repack when a parameter was replaced / cast / written in place
+        if self._engine is None or self._engine.device != dev or self._engine.fingerprint != fp:
+            self._engine = None
             sd = {k: v.detach().to(dev, torch.float32).contiguous() for k, v in self.predictor.state_dict().items()}
             head = {"w0": sd["decoder.0.weight"], "b0": sd["decoder.0.bias"], "lnw": sd["decoder.1.weight"],
                     "lnb": sd["decoder.1.bias"], "w4": sd["decoder.4.weight"], "b4": sd["decoder.4.bias"]}
             self._engine = GinEngine(dev, self.hidden_size, self.num_layer, True, self.out_dim, self.text_input_size, sd, head)
+            self._engine.fingerprint = fp
         return self._engine
 
     @torch.no_grad()

@@ -105,18 +105,39 @@ def unpack_graphs(wire: torch.Tensor, N: int) -> Tuple[torch.Tensor, torch.Tenso
     return X, E, n
 
 
+def _comm_device(group=None) -> torch.device:
+    """Device the collectives of `group` need their tensors on (NCCL: this rank's GPU; gloo: host)."""
+    if dist.is_available() and dist.is_initialized() and "nccl" in str(dist.get_backend(group)).lower():
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
 def sample_graphs_sharded(generate_fn: Callable, properties: torch.Tensor, text_embedding: torch.Tensor, n_nodes: torch.Tensor,
-                          seed: int = 0, group=None, wire: str = "compact", **kw):
+                          seed: int = 0, group=None, wire: str = "compact", max_nodes: Optional[int] = None, **kw):
     """Shard a sampling batch over the ranks and gather the integer graphs.
 
     generate_fn(properties, text_embedding, n_nodes=..., seed=..., mol_index_base=...) -> (X, E, n) as
     GraphDiT.generate_graphs.  Every rank passes the FULL batch and receives the FULL result.  The one exchange is an
     all-gather of the compact byte rows of pack_graphs (`wire="full"` gathers the int64 tensors instead).
+
+    A batch smaller than the world size leaves some ranks with an EMPTY shard (the tail chunk of a ConditionQueue flush,
+    e.g. 2050 molecules in chunks of 2048 on 8 GPUs): such a rank does not call generate_fn at all (the sampler has no B=0
+    launch) and joins the all-gather with zero rows; it needs `max_nodes` (or a bound `GraphDiT.generate_graphs`, whose
+    module carries it) to shape them.
     """
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     s, e = shard_range(properties.shape[0], rank, world)
-    X, E, n = generate_fn(properties[s:e], text_embedding[s:e], n_nodes=n_nodes[s:e], seed=seed, mol_index_base=s, **kw)
+    if e > s:
+        X, E, n = generate_fn(properties[s:e], text_embedding[s:e], n_nodes=n_nodes[s:e], seed=seed, mol_index_base=s, **kw)
+    else:
+        N = max_nodes if max_nodes is not None else getattr(getattr(generate_fn, "__self__", None), "max_n_nodes", None)
+        if N is None:
+            raise ValueError("sample_graphs_sharded: this rank's shard is empty (batch < world size); pass max_nodes=")
+        dev = _comm_device(group)
+        X = torch.zeros((0, int(N)), dtype=torch.int64, device=dev)
+        E = torch.zeros((0, int(N), int(N)), dtype=torch.int64, device=dev)
+        n = torch.zeros((0,), dtype=torch.int64, device=dev)
     if world == 1:
         return X, E, n
     if wire == "full":

@@ -32,3 +32,19 @@ def dit_small():
 @pytest.fixture(scope="session")
 def gin_small():
     return load_golden("gin_small.pt")
+
+
+def record_parity(name, **metrics):
+    """Append one measured parity result to gpurun_out/parity.json (or $LLB_PARITY_OUT): the numbers DESIGN.md quotes are
+    kept as an artefact of the run that produced them (copied to profiles/parity_r*.json)."""
+    import json
+
+    path = os.environ.get("LLB_PARITY_OUT", os.path.join(ROOT, "gpurun_out", "parity.json"))
+    try:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        data = json.load(open(path)) if os.path.exists(path) else {}
+        data[name] = {k: (float(v) if isinstance(v, (int, float)) else v) for k, v in metrics.items()}
+        with open(path, "w") as f:
+            json.dump(data, f, indent=1, sort_keys=True)
+    except Exception:
+        pass

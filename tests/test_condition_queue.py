@@ -208,7 +208,34 @@ def test_queue_sharded_world2():
     assert all(g[2] <= 3 for g in got)      # chunks of 5 molecules are split over the two ranks
 
 
+def test_flush_failure_keeps_the_queue():
+    """A sampler failure in the middle of a flush (out of memory, a collective error) must not lose any request: the
+    queue is untouched and a later flush delivers everything."""
+    fake = _FakeDit()
+    boom = {"left": 1}
+
+    def flaky(*a, **k):
+        if boom["left"] > 0 and len(fake.calls) == 1:   # fail on the SECOND chunk of the first flush
+            boom["left"] -= 1
+            raise RuntimeError("CUDA out of memory (simulated)")
+        return fake.generate_graphs(*a, **k)
+
+    q = ConditionQueue(fake, max_batch=4, seed=1, generate_fn=flaky)
+    reqs = _requests([3, 4, 2])
+    tickets = [q.submit(p, t) for p, t in reqs]
+    with pytest.raises(RuntimeError):
+        q.flush()
+    assert q.pending() == 9
+    assert q.flush() == 9 and q.pending() == 0
+    ref = ConditionQueue(_FakeDit(), max_batch=4, seed=1)
+    rt = [ref.submit(p, t) for p, t in reqs]
+    for a, b in zip(tickets, rt):
+        for u, v in zip(q.result(a), ref.result(b)):
+            assert torch.equal(u, v)
+
+
 # ------------------------------------------------------------------------------------------------ property test
+pytest.importorskip("hypothesis")
 from hypothesis import given, settings  # noqa: E402
 from hypothesis import strategies as st  # noqa: E402
 

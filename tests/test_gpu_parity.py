@@ -704,3 +704,60 @@ def test_sampler_is_deterministic_on_the_fused_throughput_path():
     X, E = eng.get_state()
     torch.cuda.synchronize()
     assert torch.equal(X, ref[0][cut:]) and torch.equal(E, ref[1][cut:])
+
+
+def test_gin_rejects_out_of_range_inputs_like_the_reference():
+    """ids / indices out of range raise IndexError (the reference's nn.Embedding / scatter do), and the kernels stay in
+    bounds while detecting it (graph_ptr used to be written past num_graphs for an unsorted `batch`)."""
+    L, H = 2, 128
+    enc, proj = synth.gin_encoder_state_dicts(L, H, seed=2)
+    g = GraphCLIP(L, H, 0.0, {})
+    g.molecule_encoder.load_state_dict(enc)
+    g.molecule_projection.load_state_dict(proj)
+    g = g.to(DEV)
+    x, ei, ea, b = synth.molecular_graphs(6, seed=1, min_nodes=3, max_nodes=9)
+    good = g(x, ei, ea, b)
+    bad_x = x.clone(); bad_x[2] = 118
+    bad_b = b.clone(); bad_b[0] = 3            # not ascending
+    bad_e = ei.clone(); bad_e[0, 1] = x.numel()
+    bad_a = ea.clone(); bad_a[0] = 5
+    for args in ((bad_x, ei, ea, b), (x, ei, ea, bad_b), (x, bad_e, ea, b), (x, ei, bad_a, b)):
+        with pytest.raises(IndexError):
+            g(*args)
+    huge_b = b.clone(); huge_b[-1] = 10 ** 6      # num_graphs taken from batch[-1]: one graph id jumps far ahead -- still in bounds
+    eng = g.engine()
+    with pytest.raises(IndexError):
+        eng.bind(x, ei, ea, torch.flip(b, [0]), num_graphs=6)
+    again = g(x, ei, ea, b)
+    torch.cuda.synchronize()
+    assert torch.equal(good, again)
+    del huge_b
+
+
+def test_engine_repacks_when_parameters_change():
+    """load_state_dict / in-place writes / dtype casts after the first forward must not leave a stale packed blob."""
+    L, H = 2, 128
+    enc, proj = synth.gin_encoder_state_dicts(L, H, seed=2)
+    enc2, proj2 = synth.gin_encoder_state_dicts(L, H, seed=3)
+    x, ei, ea, b = synth.molecular_graphs(4, seed=1, min_nodes=3, max_nodes=9)
+    g = GraphCLIP(L, H, 0.0, {})
+    g.molecule_encoder.load_state_dict(enc)
+    g.molecule_projection.load_state_dict(proj)
+    g = g.to(DEV)
+    a = g(x, ei, ea, b)
+    g.molecule_encoder.load_state_dict(enc2)
+    g.molecule_projection.load_state_dict(proj2)
+    b2 = g(x, ei, ea, b)
+    fresh = GraphCLIP(L, H, 0.0, {})
+    fresh.molecule_encoder.load_state_dict(enc2)
+    fresh.molecule_projection.load_state_dict(proj2)
+    ref = fresh.to(DEV)(x, ei, ea, b)
+    assert not torch.equal(a, b2) and torch.equal(b2, ref)
+    with torch.no_grad():
+        g.molecule_encoder.atom_encoder.weight.mul_(0.5)      # in-place write
+    c = g(x, ei, ea, b)
+    assert not torch.equal(c, b2)
+    for p in g.parameters():                                  # the reference loader's cast loop (loader.py:245-247)
+        p.data = p.data.to(torch.bfloat16)
+    d = g(x, ei, ea, b)
+    assert d.dtype == torch.bfloat16 and bool(torch.isfinite(d.float()).all())

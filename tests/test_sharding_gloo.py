@@ -47,6 +47,21 @@ def _worker(rank, world, port, q):
         X, E, n = sharding.sample_graphs_sharded(gen, props, txt, n_nodes, seed=3)
         Xf, Ef, nf = gen(props, txt, n_nodes, 3, 0)
         ok_dit = torch.equal(X, Xf) and torch.equal(E, Ef) and torch.equal(n, nf)
+
+        # a batch SMALLER than the world: rank 1's shard is empty; it must not call the sampler (which has no B = 0 launch)
+        # and must still join the all-gather with zero rows (this used to hang the other ranks)
+        calls = []
+
+        def gen1(props, txt, n_nodes, seed, mol_index_base):
+            assert props.shape[0] >= 1, "the sampler must never be called on an empty shard"
+            calls.append(props.shape[0])
+            return gen(props, txt, n_nodes, seed, mol_index_base)
+
+        for wire in ("compact", "full"):
+            X1, E1, n1 = sharding.sample_graphs_sharded(gen1, props[:1], txt[:1], n_nodes[:1], seed=3, max_nodes=5, wire=wire)
+            Xs, Es, ns = gen(props[:1], txt[:1], n_nodes[:1], 3, 0)
+            ok_dit = ok_dit and torch.equal(X1, Xs) and torch.equal(E1, Es) and torch.equal(n1, ns)
+        ok_dit = ok_dit and len(calls) == (2 if rank == 0 else 0)
         q.put((rank, ok_enc, ok_dit))
     finally:
         dist.destroy_process_group()

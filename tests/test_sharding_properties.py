@@ -1,10 +1,13 @@
 """Property tests (hypothesis) of the multi-GPU host logic: every unit is owned by exactly one rank, graph ranges are
 contiguous and cover the batch, the sub-batch split keeps edges inside their graphs, and the wire format is lossless."""
+import pytest
 import torch
-from hypothesis import given, settings
-from hypothesis import strategies as st
 
-from llamole_b200 import sharding, synth
+pytest.importorskip("hypothesis")
+from hypothesis import given, settings  # noqa: E402
+from hypothesis import strategies as st  # noqa: E402
+
+from llamole_b200 import sharding, synth  # noqa: E402
 
 
 @settings(max_examples=200, deadline=None)
