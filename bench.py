@@ -240,6 +240,7 @@ def main():
     ap.add_argument("--no-predictor", action="store_true")
     ap.add_argument("--small", action="store_true", help="tiny model (debug only; invalid as a benchmark)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--only", default="", choices=["", "gin", "predictor"], help="development: time one GIN sub-benchmark alone and print its object")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -274,6 +275,14 @@ def main():
 
     pk = peaks()
     T = DIT["T"]
+    if args.only:
+        fn = bench_gin if args.only == "gin" else bench_predictor
+        out = fn(args, device, rank, world, barrier, max_over_ranks, pk)
+        if rank == 0:
+            print(json.dumps(out), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     # ------------------------------------------------------------------ GraphDiT
     m, cfg, meta, sd = build_dit(device, small=args.small)
     eng = m.engine()

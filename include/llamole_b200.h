@@ -52,7 +52,7 @@ enum {
   LLB_PROF_GEMM_QKV = 0, LLB_PROF_GEMM_PROJ, LLB_PROF_GEMM_FC1, LLB_PROF_GEMM_FC2, LLB_PROF_GEMM_ADALN,
   LLB_PROF_GEMM_OTHER, LLB_PROF_ATTENTION, LLB_PROF_LN_MOD_RES, LLB_PROF_DIT_STEP, LLB_PROF_DIT_MISC,
   LLB_PROF_GIN_AGGREGATE, LLB_PROF_GIN_POOL, LLB_PROF_GIN_GEMM_MLP0, LLB_PROF_GIN_GEMM_MLP4, LLB_PROF_GIN_ROWLN,
-  LLB_PROF_GIN_MISC, LLB_PROF_GIN_GEMM_HEAD, LLB_PROF_GIN_TOPK, LLB_PROF_SLOTS
+  LLB_PROF_GIN_MISC, LLB_PROF_GIN_GEMM_HEAD, LLB_PROF_GIN_TOPK, LLB_PROF_GIN_GEMM_STATS, LLB_PROF_SLOTS
 };
 int llb_profile_enable(int on);
 int llb_profile_read(int slot, double* total_ms, int64_t* launches);

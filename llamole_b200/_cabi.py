@@ -169,7 +169,7 @@ def kernel_launches(family: int) -> int:
     return int(lib().llb_kernel_launches(int(family)))
 
 
-PROF_SLOTS = 18
+PROF_SLOTS = 19
 
 
 def profile_enable(on: bool) -> None:

@@ -70,6 +70,18 @@ struct epi_no_store : std::false_type {};
 template <class E>
 struct epi_no_store<E, std::void_t<decltype(E::NO_STORE)>> : std::integral_constant<bool, E::NO_STORE> {};
 
+// Epilogue functors may carry per-ROW state across the column chunks of a tile (a running reduction, a row statistic looked up
+// once): they declare `struct RowState` and the three-call protocol below.
+template <class E, class = void>
+struct epi_row_state : std::false_type {};
+template <class E>
+struct epi_row_state<E, std::void_t<typename E::RowState>> : std::true_type {};
+struct EpiNoRowState {};
+template <class E, bool HAS = epi_row_state<E>::value>
+struct epi_row_state_of { using type = EpiNoRowState; };
+template <class E>
+struct epi_row_state_of<E, true> { using type = typename E::RowState; };
+
 // One epilogue warp's share of a 128 x BN accumulator tile: warp % 4 selects the TMEM lane quarter (32 rows), the
 // warps sharing a quarter split the columns.  tcgen05.ld -> fused functor -> swizzled smem staging -> TMA store.
 template <int BN, bool TMA_STORE, class Epi>
@@ -79,11 +91,14 @@ __device__ __forceinline__ void gemm_epilogue_tile(const Epi& epi, const CUtenso
   constexpr int ROW_BYTES = Epi::CHUNK * ELEM;
   constexpr int NBUF = GEMM_STAGING_PER_WARP / (32 * ROW_BYTES);
   constexpr int COLS_PER_WARP = BN / (GEMM_EPI_WARPS / 4);
+  constexpr bool ROW_STATE = epi_row_state<Epi>::value;
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int quarter = warp & 3, cg = warp >> 2;
   const int row = m0 + quarter * 32 + lane;
   const uint32_t t_row = tmem_acc + ((uint32_t)(quarter * 32) << 16) + cg * COLS_PER_WARP;
   float v[Epi::CHUNK];
+  typename epi_row_state_of<Epi>::type rst;
+  if constexpr (ROW_STATE) rst = epi.row_begin(row, M);
 #pragma unroll 1
   for (int c = 0; c < COLS_PER_WARP; c += Epi::CHUNK) {
     const int col0 = n0 + cg * COLS_PER_WARP + c;
@@ -91,7 +106,10 @@ __device__ __forceinline__ void gemm_epilogue_tile(const Epi& epi, const CUtenso
     tmem_ld32(t_row + c, v);
     if (Epi::CHUNK == 64) tmem_ld32(t_row + c + 32, v + 32);
     tmem_ld_wait();
-    if (!LLB_EXP(4)) epi.transform(row, col0, v, M, N);
+    if (!LLB_EXP(4)) {
+      if constexpr (ROW_STATE) epi.transform(row, col0, v, M, N, rst);
+      else epi.transform(row, col0, v, M, N);
+    }
     if (LLB_EXP(8) || epi_no_store<Epi>::value) continue;
     if (TMA_STORE) {
       uint8_t* dst = stg + buf * (32 * ROW_BYTES);
@@ -131,6 +149,8 @@ __device__ __forceinline__ void gemm_epilogue_tile(const Epi& epi, const CUtenso
       }
     }
   }
+  // slot = which (N tile, column group) of the row this warp covered: (N / BN rounded up) * (epilogue warps / 4) slots per row
+  if constexpr (ROW_STATE) epi.row_end(row, (n0 / BN) * (GEMM_EPI_WARPS / 4) + cg, rst, M);
 }
 
 // Epilogue functor contract:
@@ -139,6 +159,8 @@ __device__ __forceinline__ void gemm_epilogue_tile(const Epi& epi, const CUtenso
 //   void* C; int ldc;              output matrix (row-major)
 //   __device__ void transform(int row, int col0, float* v, int M, int N) const   -- in place on v[CHUNK];
 //     called for every row of the tile, including rows >= M (their results are never stored).
+//   optional per-row state (struct RowState): RowState row_begin(row, M); transform(..., RowState&); row_end(row, slot, RowState&, M)
+//     -- row_begin once per (tile, thread) before the first chunk, row_end after the last one, slot as computed above.
 template <int BN, bool TMA_STORE, class Epi>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -602,9 +624,9 @@ int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, in
 // ------------------------------------------------------------------------------------------------
 // Epilogues
 // ------------------------------------------------------------------------------------------------
-template <int ACT>
+template <int ACT, bool F32 = true>
 __device__ __forceinline__ float apply_act(float x) {
-  if (ACT == LLB_ACT_GELU) return gelu_fast(x);
+  if (ACT == LLB_ACT_GELU) return F32 ? gelu_fast(x) : gelu_bf16(x);   // bf16 output: the cheaper fit is far below the rounding
   if (ACT == 9) return gelu_fma_only(x);   // experiment variants (tools/gemm_trace.cu only)
   if (ACT == 10) {
     float y = x;
@@ -639,7 +661,7 @@ struct EpiBiasAct {
       }
     }
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = apply_act<ACT>(v[i]);
+    for (int i = 0; i < 32; ++i) v[i] = apply_act<ACT, F32>(v[i]);
   }
 };
 

@@ -5,6 +5,7 @@
 // (bf16 copy: the gather source of the aggregation and nothing else).  Edges are a destination-sorted CSR
 // (rowptr/col/etype), graphs are contiguous node ranges (graph_ptr), so every reduction (neighbour sum,
 // per-graph max / sum pooling) is a segmented loop with no atomics.
+#include <math.h>
 #include <stdlib.h>
 
 #include <vector>
@@ -21,8 +22,10 @@ constexpr int BOND_VOCAB = 5;
 struct GinLayout {
   int H, L, predictor, out_dim, tdim, HH, HO;
   std::vector<size_t> mlp0_w, mlp4_w, vn0_w, vn4_w, adapter_w;   // bf16
-  std::vector<size_t> mlp_gram;                                    // bf16 (H,H): W0^T W0 of the bf16 node-MLP weight (analytic LayerNorm statistics)
-  std::vector<size_t> mlp_stat;                                    // fp32 [wbar (H) | 2 W0^T b (H) | bbar, |b|^2 / 4H, 0, 0]
+  std::vector<size_t> mlp_chol;                                    // bf16 (H,H): Cholesky factor of the node MLP's first linear (analytic LayerNorm)
+  std::vector<size_t> mlp_stat;                                    // fp32 [r (H) | c0, 0, 0, 0]: bias column and constant of that factor
+  std::vector<size_t> mlp_bg;                                      // fp32 (4H): centred bias x LayerNorm gamma
+  size_t chol_scratch;                                             // fp64 (H+1, H+1) Gram matrix, pack time only
   size_t head0_w, head4_w;
   size_t atom_emb, vn_emb, text_drop;                             // fp32
   std::vector<size_t> eps, mlp0_b, mlp_ln_w, mlp_ln_b, mlp4_b, bond_emb, norm_w, norm_b;
@@ -49,7 +52,7 @@ int make_layout(const llb_gin_config& c, GinLayout& G) {
   for (int l = 0; l < G.L; ++l) {
     G.mlp0_w.push_back(take(4 * H * H * 2));
     G.mlp4_w.push_back(take(4 * H * H * 2));
-    G.mlp_gram.push_back(take(H * H * 2));
+    G.mlp_chol.push_back(take(H * H * 2));
     if (l < G.L - 1) {
       G.vn0_w.push_back(take(4 * H * H * 2));
       G.vn4_w.push_back(take(4 * H * H * 2));
@@ -65,7 +68,8 @@ int make_layout(const llb_gin_config& c, GinLayout& G) {
     G.eps.push_back(take(4));
     G.mlp0_b.push_back(take(4 * H * 4)), G.mlp_ln_w.push_back(take(4 * H * 4)), G.mlp_ln_b.push_back(take(4 * H * 4));
     G.mlp4_b.push_back(take(H * 4));
-    G.mlp_stat.push_back(take((2 * H + 4) * 4));
+    G.mlp_stat.push_back(take((H + 4) * 4));
+    G.mlp_bg.push_back(take(4 * H * 4));
     G.bond_emb.push_back(take(BOND_VOCAB * H * 4));
     G.norm_w.push_back(take(H * 4)), G.norm_b.push_back(take(H * 4));
     if (l < G.L - 1) {
@@ -76,6 +80,7 @@ int make_layout(const llb_gin_config& c, GinLayout& G) {
   }
   G.head0_b = take((size_t)G.HH * 4), G.head_ln_w = take((size_t)G.HH * 4), G.head_ln_b = take((size_t)G.HH * 4);
   G.head4_b = take((size_t)G.HO * 4);
+  G.chol_scratch = take((H + 1) * (H + 1) * 8);
   G.total = align_up(off, 256);
   return LLB_OK;
 }
@@ -229,10 +234,10 @@ __global__ void __launch_bounds__(256) gin_aggregate_kernel(const float* __restr
       const uint4 u = *reinterpret_cast<const uint4*>(hb + (size_t)j * H + c);
       const float4 e0 = *reinterpret_cast<const float4*>(bond_emb + (size_t)et * H + c);
       const float4 e1 = *reinterpret_cast<const float4*>(bond_emb + (size_t)et * H + c + 4);
-      acc[0] += gelu_fast(bf16_lo(u.x) + e0.x), acc[1] += gelu_fast(bf16_hi(u.x) + e0.y);
-      acc[2] += gelu_fast(bf16_lo(u.y) + e0.z), acc[3] += gelu_fast(bf16_hi(u.y) + e0.w);
-      acc[4] += gelu_fast(bf16_lo(u.z) + e1.x), acc[5] += gelu_fast(bf16_hi(u.z) + e1.y);
-      acc[6] += gelu_fast(bf16_lo(u.w) + e1.z), acc[7] += gelu_fast(bf16_hi(u.w) + e1.w);
+      acc[0] += gelu_bf16(bf16_lo(u.x) + e0.x), acc[1] += gelu_bf16(bf16_hi(u.x) + e0.y);
+      acc[2] += gelu_bf16(bf16_lo(u.y) + e0.z), acc[3] += gelu_bf16(bf16_hi(u.y) + e0.w);
+      acc[4] += gelu_bf16(bf16_lo(u.z) + e1.x), acc[5] += gelu_bf16(bf16_hi(u.z) + e1.y);
+      acc[6] += gelu_bf16(bf16_lo(u.w) + e1.z), acc[7] += gelu_bf16(bf16_hi(u.w) + e1.w);
     }
     *reinterpret_cast<uint4*>(out + (size_t)i * H + c) =
         make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
@@ -241,117 +246,157 @@ __global__ void __launch_bounds__(256) gin_aggregate_kernel(const float* __restr
 
 // ---------------------------------------------------------------------------------------------
 // Analytic LayerNorm statistics for the node MLP (Linear(H,4H) -> LayerNorm(4H) -> GELU -> Linear(4H,H), model.py:156-165).
-// The LayerNorm needs the mean and variance of a 4H-wide row z = W a + b that no single CTA holds, which is why the
-// unfused path writes z (757 MB per layer for 123 k nodes), re-reads and rewrites it in a row kernel and reads it again
-// in the second GEMM.  Both moments are functions of the H-wide INPUT row a:
-//     mean = a . wbar + bbar                                 wbar = column mean of W, bbar = mean of b
-//     E[z^2] = (a^T G a + 2 a . (W^T b) + |b|^2) / 4H        G = W^T W  (H x H, symmetric)
-// G, wbar, W^T b are computed once at pack time from the bf16-rounded W (what the tensor core multiplies by).  Per layer
-// one extra (n, H) x (H, H) GEMM -- a quarter of the first linear -- whose epilogue never stores its product: thread = row
-// takes the dot of its 32 accumulator columns (+ 2 W^T b / 4H) with the row's own a values, and a . wbar, into a
-// (n, H/32, 2) partial buffer; gin_ln_stats_kernel adds the partials in column order -> (mean, rstd) per row.  The first
-// linear's epilogue then applies LayerNorm + affine + GELU directly (EpiLnGelu), so z never exists un-normalised.
-// Numerics (tools/ln_analytic_study.py): against the two-pass LayerNorm the error of GELU(LN(z)) is 6e-4 max / 4e-5 rms
-// with G in bf16, 25x below the bf16 rounding of that output.
+// The LayerNorm needs the mean and variance of a 4H-wide row z = W a + b that no single CTA holds (3072 fp32 accumulator
+// columns against 512 of tensor memory), which is why the unfused path writes z (757 MB per layer for 123 k nodes), re-reads
+// and rewrites it in a row kernel and reads it again in the second GEMM.  Both moments are functions of the H-wide INPUT row a:
+//   * mean.  LayerNorm is invariant to a shift of its input, so the weight is CENTRED over its 4H outputs at pack time,
+//     Wc = W - 1 wbar^T, bc = b - bbar: zc = Wc a + bc has zero mean by construction and LN(zc) = LN(z).  (The bf16 rounding of
+//     Wc leaves a residual mean of ~1e-4 sigma, which is ignored.)
+//   * variance.  |zc|^2 = |Wt at|^2 with the augmented Wt = [Wc | bc] (4H x (H+1)) and at = [a; 1].  With the Cholesky factor
+//     Wt^T Wt = Rt^T Rt (upper triangular, fp64 on the host at pack time, from the bf16-rounded Wc the tensor core multiplies by)
+//     |zc|^2 = |Rt at|^2 = sum_{k<H} (R[k,:] . a + r[k])^2 + c0,   R = Rt[:H,:H], r = Rt[:H,H], c0 = Rt[H,H]^2,
+//     i.e. ONE extra (n,H) x (H,H) GEMM per layer (a quarter of the first linear) whose epilogue only squares and adds its
+//     accumulators (EpiRowSq: no output matrix, no operand re-reads) into (n, 6) partial sums.
+// The first linear's epilogue (EpiLnGelu) then turns a row's partial sums into rstd and applies LayerNorm + affine + GELU
+// directly, so z never exists un-normalised and the row kernel over the 4H-wide matrix disappears.
+// Numerics (tests/test_analytic_ln_numerics.py): against the fp64-weight result the error of GELU(LN(z)) is the same as that of
+// the two-pass LayerNorm on bf16 weights (rms 1.2e-3 = the bf16 rounding of the weights); rstd itself is within 4e-4.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gin_gram_kernel(const __nv_bfloat16* __restrict__ W, int rows, int H, __nv_bfloat16* __restrict__ Gm) {
-  // Gm[i][j] = sum_o W[o][i] W[o][j]; one thread per (i, j), pack time only
-  const int j = blockIdx.x * 16 + (threadIdx.x & 15), i = blockIdx.y * 16 + (threadIdx.x >> 4);
-  if (i >= H || j >= H) return;
-  float acc = 0.f;
-  for (int o = 0; o < rows; ++o) acc = fmaf(__bfloat162float(W[(size_t)o * H + i]), __bfloat162float(W[(size_t)o * H + j]), acc);
-  Gm[(size_t)i * H + j] = __float2bfloat16(acc);
-}
-__global__ void __launch_bounds__(256) gin_stat_vectors_kernel(const __nv_bfloat16* __restrict__ W, const float* __restrict__ b, int rows, int H,
-                                                               float* __restrict__ out) {
-  // out = [wbar (H) | 2 W^T b (H) | bbar, |b|^2 / rows, 0, 0]
+__global__ void __launch_bounds__(256) gin_colmean_kernel(const float* __restrict__ W, int rows, int H, float* __restrict__ wbar) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < H) {
-    float sw = 0.f, sc = 0.f;
-    for (int o = 0; o < rows; ++o) {
-      const float w = __bfloat162float(W[(size_t)o * H + k]);
-      sw += w;
-      sc = fmaf(w, b[o], sc);
-    }
-    out[k] = sw / rows;
-    out[H + k] = 2.0f * sc;
+  if (k >= H) return;
+  double s = 0.0;
+  for (int o = 0; o < rows; ++o) s += (double)W[(size_t)o * H + k];
+  wbar[k] = (float)(s / rows);
+}
+__global__ void gin_center_weight_kernel(const float* __restrict__ W, const float* __restrict__ wbar, int rows, int H,
+                                         __nv_bfloat16* __restrict__ out) {
+  const size_t total = (size_t)rows * H;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x)
+    out[idx] = __float2bfloat16(W[idx] - wbar[idx % H]);
+}
+// bc = b - mean(b), bg = bc * gamma (one block)
+__global__ void __launch_bounds__(1024) gin_center_bias_kernel(const float* __restrict__ b, const float* __restrict__ gamma, int rows,
+                                                               float* __restrict__ bc, float* __restrict__ bg) {
+  __shared__ double red[32];
+  __shared__ double s_mean;
+  double s = 0.0;
+  for (int o = threadIdx.x; o < rows; o += blockDim.x) s += (double)b[o];
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    s_mean = t / rows;
   }
-  if (k == 0) {
-    float sb = 0.f, sbb = 0.f;
-    for (int o = 0; o < rows; ++o) sb += b[o], sbb = fmaf(b[o], b[o], sbb);
-    out[2 * H] = sb / rows, out[2 * H + 1] = sbb / rows, out[2 * H + 2] = 0.f, out[2 * H + 3] = 0.f;
+  __syncthreads();
+  const float m = (float)s_mean;
+  for (int o = threadIdx.x; o < rows; o += blockDim.x) {
+    const float c = b[o] - m;
+    bc[o] = c;
+    bg[o] = c * gamma[o];
+  }
+}
+// Gram matrix of the augmented weight Wt = [Wc (bf16) | bc] in fp64: Gm (H+1, H+1), one thread per entry, pack time only.
+__global__ void __launch_bounds__(256) gin_gram64_kernel(const __nv_bfloat16* __restrict__ Wc, const float* __restrict__ bc, int rows, int H,
+                                                         double* __restrict__ Gm) {
+  const int j = blockIdx.x * 16 + (threadIdx.x & 15), i = blockIdx.y * 16 + (threadIdx.x >> 4);
+  if (i > H || j > H || j < i) return;   // upper triangle; the host mirrors it
+  double acc = 0.0;
+  for (int o = 0; o < rows; ++o) {
+    const double wi = i < H ? (double)__bfloat162float(Wc[(size_t)o * H + i]) : (double)bc[o];
+    const double wj = j < H ? (double)__bfloat162float(Wc[(size_t)o * H + j]) : (double)bc[o];
+    acc = fma(wi, wj, acc);
+  }
+  Gm[(size_t)i * (H + 1) + j] = acc;
+}
+
+// Host: lower Cholesky factor L of the symmetric positive (semi-)definite matrix whose UPPER triangle is in Gm (n x n), in place
+// in Lm (row-major, L[i][j] for j <= i).  Row-oriented (Cholesky-Crout): both operands of every dot product are contiguous.
+static void cholesky_lower_host(const std::vector<double>& Gm, int n, std::vector<double>& Lm) {
+  Lm.assign((size_t)n * n, 0.0);
+  double trace = 0.0;
+  for (int i = 0; i < n; ++i) trace += Gm[(size_t)i * n + i];
+  const double floor_d = 1e-14 * (trace / n) + 1e-300;
+  for (int i = 0; i < n; ++i) {
+    double* Li = &Lm[(size_t)i * n];
+    for (int j = 0; j <= i; ++j) {
+      const double* Lj = &Lm[(size_t)j * n];
+      double s = Gm[(size_t)j * n + i];   // G[j][i], j <= i: upper triangle
+      for (int k = 0; k < j; ++k) s -= Li[k] * Lj[k];
+      if (j < i) Li[j] = s / Lj[j];
+      else Li[i] = sqrt(s > floor_d ? s : floor_d);   // a rank-deficient weight gets a harmless tiny pivot
+    }
   }
 }
 
-// Epilogue of the statistics GEMM S = a G: no matrix output.
-struct EpiRowStats {
+// Epilogue of the statistics GEMM Y = a R^T: no matrix output, per row the sum of (Y + r)^2 over the warp's columns.
+struct EpiRowSq {
   static constexpr int CHUNK = 32;
   static constexpr bool OUT_F32 = true;
   static constexpr bool NO_STORE = true;
   void* C;     // unused
   int ldc;     // unused
-  const __nv_bfloat16* A;   // (M, lda) the GEMM's own A operand
-  int lda;
-  const float* stat;        // [wbar (N) | 2 W^T b (N) | ...]
-  float2* part;             // (M, N / 32) partial (a . (S + 2 W^T b), a . wbar) over 32 columns
-  __device__ __forceinline__ void transform(int row, int col0, float* v, int M, int N) const {
-    if (row >= M) return;
-    const uint4* ap = reinterpret_cast<const uint4*>(A + (size_t)row * lda + col0);
-    float q = 0.f, m = 0.f;
+  const float* r;   // (N) bias column of the factor
+  float* part;      // (M, slots) partial sums, slot = (N tile, column group)
+  int slots;
+  struct RowState {
+    float q;
+  };
+  __device__ __forceinline__ RowState row_begin(int, int) const { return RowState{0.f}; }
+  __device__ __forceinline__ void transform(int, int col0, float* v, int, int, RowState& st) const {
+    float q0 = 0.f, q1 = 0.f;   // two chains: the 32 dependent FMAs would otherwise serialise on the 4-cycle FMA latency
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint4 u = __ldg(ap + i);
-      const float a8[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y), bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
-      const float4 w0 = __ldg(reinterpret_cast<const float4*>(stat + col0 + 8 * i)), w1 = __ldg(reinterpret_cast<const float4*>(stat + col0 + 8 * i + 4));
-      const float4 c0 = __ldg(reinterpret_cast<const float4*>(stat + N + col0 + 8 * i)), c1 = __ldg(reinterpret_cast<const float4*>(stat + N + col0 + 8 * i + 4));
-      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-      const float cv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        q = fmaf(a8[e], v[8 * i + e] + cv[e], q);   // a . (G a + 2 W^T b); the finaliser divides by the 4H rows of W
-        m = fmaf(a8[e], wv[e], m);                  // a . wbar
-      }
+    for (int i = 0; i < 32; i += 8) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(r + col0 + i)), b = __ldg(reinterpret_cast<const float4*>(r + col0 + i + 4));
+      const float t0 = v[i] + a.x, t1 = v[i + 1] + a.y, t2 = v[i + 2] + a.z, t3 = v[i + 3] + a.w;
+      const float t4 = v[i + 4] + b.x, t5 = v[i + 5] + b.y, t6 = v[i + 6] + b.z, t7 = v[i + 7] + b.w;
+      q0 = fmaf(t0, t0, q0), q1 = fmaf(t4, t4, q1);
+      q0 = fmaf(t1, t1, q0), q1 = fmaf(t5, t5, q1);
+      q0 = fmaf(t2, t2, q0), q1 = fmaf(t6, t6, q1);
+      q0 = fmaf(t3, t3, q0), q1 = fmaf(t7, t7, q1);
     }
-    part[(size_t)row * (N / 32) + col0 / 32] = make_float2(q, m);
+    st.q += q0 + q1;
+  }
+  __device__ __forceinline__ void row_end(int row, int slot, RowState& st, int M) const {
+    if (row < M) part[(size_t)row * slots + slot] = st.q;
   }
 };
 
-__global__ void __launch_bounds__(256) gin_ln_stats_kernel(const float2* __restrict__ part, int n, int chunks, const float* __restrict__ stat, int H,
-                                                           float inv_rows, float2* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float q = 0.f, m = 0.f;
-  for (int c = 0; c < chunks; ++c) {   // column order: deterministic
-    const float2 p = part[(size_t)i * chunks + c];
-    q += p.x, m += p.y;
-  }
-  const float mean = m + stat[2 * H];
-  const float ez2 = q * inv_rows + stat[2 * H + 1];
-  const float var = fmaxf(ez2 - mean * mean, 0.f);
-  out[i] = make_float2(mean, rsqrtf(var + 1e-5f));
-}
-
-// Epilogue of the first linear with the row statistics known: GELU(LayerNorm(acc + bias) * gamma + beta) -> bf16.
+// Epilogue of the first linear (centred weight) with the row's |zc|^2 known: GELU(zc * rstd * gamma + beta) -> bf16.
 struct EpiLnGelu {
   static constexpr int CHUNK = 32;
   static constexpr bool OUT_F32 = false;
   void* C;
   int ldc;
-  const float *bias, *gamma, *beta;   // (N)
-  const float2* stats;                // (M) mean, rstd
-  __device__ __forceinline__ void transform(int row, int col0, float* v, int M, int N) const {
-    const float2 st = row < M ? __ldg(stats + row) : make_float2(0.f, 1.f);
+  const float *gamma, *bgamma, *beta;   // (N): LayerNorm weight, centred bias x weight, LayerNorm bias
+  const float* part;                    // (M, slots) from EpiRowSq
+  int slots;
+  float c0, inv_rows;                   // constant of the factor, 1 / 4H
+  struct RowState {
+    float rstd;
+  };
+  __device__ __forceinline__ RowState row_begin(int row, int M) const {
+    float q = c0;
+    if (row < M)
+      for (int s = 0; s < slots; ++s) q += __ldg(part + (size_t)row * slots + s);   // slot order: deterministic
+    return RowState{rsqrtf(q * inv_rows + 1e-5f)};
+  }
+  __device__ __forceinline__ void transform(int, int col0, float* v, int, int, RowState& st) const {
+    const float rs = st.rstd;
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col0 + i));
       const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + col0 + i));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bgamma + col0 + i));
       const float4 t = __ldg(reinterpret_cast<const float4*>(beta + col0 + i));
-      v[i] = gelu_fast(fmaf((v[i] + b.x - st.x) * st.y, g.x, t.x));
-      v[i + 1] = gelu_fast(fmaf((v[i + 1] + b.y - st.x) * st.y, g.y, t.y));
-      v[i + 2] = gelu_fast(fmaf((v[i + 2] + b.z - st.x) * st.y, g.z, t.z));
-      v[i + 3] = gelu_fast(fmaf((v[i + 3] + b.w - st.x) * st.y, g.w, t.w));
+      v[i] = gelu_bf16(fmaf(rs, fmaf(v[i], g.x, b.x), t.x));
+      v[i + 1] = gelu_bf16(fmaf(rs, fmaf(v[i + 1], g.y, b.y), t.y));
+      v[i + 2] = gelu_bf16(fmaf(rs, fmaf(v[i + 2], g.z, b.z), t.z));
+      v[i + 3] = gelu_bf16(fmaf(rs, fmaf(v[i + 3], g.w, b.w), t.w));
     }
   }
+  __device__ __forceinline__ void row_end(int, int, RowState&, int) const {}
 };
 
 // Per-graph pooling over the contiguous node range (graph_encoder/model.py:148,152): max -> bf16 operand of the
@@ -729,7 +774,9 @@ struct llb_gin {
   __nv_bfloat16* agg = nullptr;
   __nv_bfloat16* z = nullptr;
   float* u = nullptr;
-  float2 *ln_part = nullptr, *ln_stats = nullptr;   // analytic LayerNorm statistics of the node MLP
+  float* ln_part = nullptr;   // (n, ln_slots) partial |zc|^2 sums of the node MLP (analytic LayerNorm)
+  int ln_slots = 0;
+  std::vector<float> chol_c0;   // per layer: constant of the Cholesky factor (host copy)
   float *vn_cur = nullptr, *vn_next = nullptr, *vu = nullptr;
   __nv_bfloat16 *pool_b = nullptr, *vz = nullptr;
   float* mod = nullptr;
@@ -760,7 +807,8 @@ static int gin_carve(llb_gin* g, void* ws, size_t ws_bytes, int n, int e, int B,
   g->h = a.take<float>((size_t)n * H), g->hb = a.take<__nv_bfloat16>((size_t)n * H), g->agg = a.take<__nv_bfloat16>((size_t)n * H);
   g->z = a.take<__nv_bfloat16>((size_t)n * 4 * H);
   g->u = a.take<float>((size_t)n * H);
-  g->ln_part = a.take<float2>((size_t)n * (H / 32)), g->ln_stats = a.take<float2>((size_t)n);   // analytic LayerNorm statistics
+  g->ln_slots = ceil_div((int)H, 256) * (GEMM_EPI_WARPS / 4);
+  g->ln_part = a.take<float>((size_t)n * g->ln_slots);   // analytic LayerNorm statistics
   g->vn_cur = a.take<float>((size_t)B * H), g->vn_next = a.take<float>((size_t)B * H), g->vu = a.take<float>((size_t)B * H);
   g->pool_b = a.take<__nv_bfloat16>((size_t)B * H), g->vz = a.take<__nv_bfloat16>((size_t)B * 4 * H);
   if (G.predictor) {
@@ -810,20 +858,15 @@ static int gin_mlp4(llb_gin* g, const __nv_bfloat16* in, int rows, size_t w0, si
   // Linear -> LayerNorm(hidden) -> GELU -> Linear  (the 4H MLP of GINConv / virtual node / heads)
   const int H = g->G.H;
   if (gram_layer >= 0) {
-    // node MLP with analytic LayerNorm statistics: statistics GEMM (no output matrix) -> per-row (mean, rstd) -> first linear
-    // with LayerNorm + GELU in its epilogue -> second linear.  The un-normalised 4H-wide intermediate never exists.
+    // node MLP with analytic LayerNorm statistics: statistics GEMM (no output matrix) -> first linear with LayerNorm + GELU in
+    // its epilogue -> second linear.  The un-normalised 4H-wide intermediate never exists.
     const GinLayout& G = g->G;
+    g->ctr.slot = LLB_PROF_GIN_GEMM_STATS;
+    EpiRowSq es{nullptr, 0, g->w<float>(G.mlp_stat[gram_layer]), g->ln_part, g->ln_slots};
+    LLB_TRY((launch_gemm<256>(in, H, g->w<void>(G.mlp_chol[gram_layer]), H, rows, H, H, es, s, &g->ctr)));
     g->ctr.slot = slot0;
-    EpiRowStats es{nullptr, 0, in, H, g->w<float>(G.mlp_stat[gram_layer]), g->ln_part};
-    LLB_TRY((launch_gemm<256>(in, H, g->w<void>(G.mlp_gram[gram_layer]), H, rows, H, H, es, s, &g->ctr)));
-    {
-      ProfScope prof(LLB_PROF_GIN_ROWLN, s);
-      gin_ln_stats_kernel<<<ceil_div(rows, 256), 256, 0, s>>>(g->ln_part, rows, H / 32, g->w<float>(G.mlp_stat[gram_layer]), H, 1.0f / (float)hidden,
-                                                              g->ln_stats);
-    }
-    LLB_CUDA_OK(cudaGetLastError());
-    g->launches++;
-    EpiLnGelu el{zbuf, hidden, g->w<float>(b0), g->w<float>(lnw), g->w<float>(lnb), g->ln_stats};
+    EpiLnGelu el{zbuf, hidden, g->w<float>(lnw), g->w<float>(G.mlp_bg[gram_layer]), g->w<float>(lnb), g->ln_part, g->ln_slots,
+                 g->chol_c0[gram_layer], 1.0f / (float)hidden};
     LLB_TRY((launch_gemm<256>(in, H, g->w<void>(w0), H, rows, hidden, H, el, s, &g->ctr)));
     g->ctr.slot = slot4;
     return gemm_bias_act(zbuf, hidden, g->w<void>(w4), hidden, g->w<float>(b4), out, out_ld, rows, out_f, hidden, LLB_ACT_NONE, true, s, &g->ctr);
@@ -887,13 +930,11 @@ static int gin_trunk(llb_gin* g, const float* c, cudaStream_t s) {
       LLB_TRY(launch_row_ln(a, s));
       g->launches++;
     }
-    // LLB_GIN_ANALYTIC_LN=1: LayerNorm + GELU in the first linear's epilogue from analytic row statistics (see EpiRowStats).
-    // Parity-green on B200 (all GIN tests; encoder embedding max |d| 2.0e-3 vs 2.8e-3 unfused) but only 1.6 % faster so far
-    // (8.70 vs 8.84 ms: row kernels -1.36 ms, statistics GEMM + heavier epilogue +1.17 ms), hence still opt-in: the
-    // statistics epilogue re-reads its A rows from L2 with 16-byte row-strided loads and is epilogue-bound at K = H.
-    static const bool analytic_ln = getenv("LLB_GIN_ANALYTIC_LN") && getenv("LLB_GIN_ANALYTIC_LN")[0] == '1';
+    // LayerNorm + GELU of the node MLP in the first linear's epilogue, from analytic row statistics (see EpiRowSq).
+    // LLB_GIN_ANALYTIC_LN=0 selects the unfused GEMM -> row kernel -> GEMM path (same centred weights: LayerNorm is shift-invariant).
+    static const bool analytic_ln = !(getenv("LLB_GIN_ANALYTIC_LN") && getenv("LLB_GIN_ANALYTIC_LN")[0] == '0');
     LLB_TRY(gin_mlp4(g, g->agg, n, G.mlp0_w[l], G.mlp0_b[l], G.mlp_ln_w[l], G.mlp_ln_b[l], G.mlp4_w[l], G.mlp4_b[l], 4 * H, H, g->z,
-                     g->u, H, s, LLB_PROF_GIN_GEMM_MLP0, LLB_PROF_GIN_GEMM_MLP4, (analytic_ln && H % 32 == 0) ? l : -1));
+                     g->u, H, s, LLB_PROF_GIN_GEMM_MLP0, LLB_PROF_GIN_GEMM_MLP4, analytic_ln ? l : -1));
     RowLnArgs a;
     a.in = g->u, a.in_ld = H, a.rows = n, a.width = H;
     a.row_group = g->batch32;
@@ -948,17 +989,41 @@ int llb_gin_pack_weights(const llb_gin_config* cfg, const llb_gin_weights* w, vo
   LLB_CUDA_OK(cp(G.atom_emb, w->atom_emb, (size_t)ATOM_VOCAB * H));
   LLB_CUDA_OK(cp(G.vn_emb, w->vn_emb, H));
   for (int l = 0; l < G.L; ++l) {
-    LLB_TRY(launch_f32_to_bf16(w->mlp0_w[l], H, bf(G.mlp0_w[l]), H, 4 * H, H, H, s));
     LLB_TRY(launch_f32_to_bf16(w->mlp4_w[l], 4 * H, bf(G.mlp4_w[l]), 4 * H, H, 4 * H, 4 * H, s));
     LLB_CUDA_OK(cp(G.eps[l], w->eps[l], 1));
-    LLB_CUDA_OK(cp(G.mlp0_b[l], w->mlp0_b[l], 4 * H));
     LLB_CUDA_OK(cp(G.mlp_ln_w[l], w->mlp_ln_w[l], 4 * H));
     LLB_CUDA_OK(cp(G.mlp_ln_b[l], w->mlp_ln_b[l], 4 * H));
     LLB_CUDA_OK(cp(G.mlp4_b[l], w->mlp4_b[l], H));
-    // analytic LayerNorm statistics of the node MLP: from the bf16-rounded weight the tensor core multiplies by
-    gin_gram_kernel<<<dim3(ceil_div(H, 16), ceil_div(H, 16)), 256, 0, s>>>(bf(G.mlp0_w[l]), 4 * H, H, bf(G.mlp_gram[l]));
-    gin_stat_vectors_kernel<<<ceil_div(H, 256), 256, 0, s>>>(bf(G.mlp0_w[l]), w->mlp0_b[l], 4 * H, H, reinterpret_cast<float*>(base + G.mlp_stat[l]));
-    LLB_CUDA_OK(cudaGetLastError());
+    // first linear of the node MLP, CENTRED over its 4H outputs (LayerNorm is shift-invariant; see EpiRowSq), and the Cholesky
+    // factor of its augmented Gram matrix for the analytic LayerNorm statistics: fp64 on the host, from the bf16-rounded
+    // weight the tensor core multiplies by.  This is the one place where pack_weights synchronises the stream.
+    {
+      float* wbar = reinterpret_cast<float*>(base + G.chol_scratch);   // scratch doubles as the column-mean buffer first
+      gin_colmean_kernel<<<ceil_div(H, 256), 256, 0, s>>>(w->mlp0_w[l], 4 * H, H, wbar);
+      gin_center_weight_kernel<<<1024, 256, 0, s>>>(w->mlp0_w[l], wbar, 4 * H, H, bf(G.mlp0_w[l]));
+      gin_center_bias_kernel<<<1, 1024, 0, s>>>(w->mlp0_b[l], w->mlp_ln_w[l], 4 * H, reinterpret_cast<float*>(base + G.mlp0_b[l]),
+                                                 reinterpret_cast<float*>(base + G.mlp_bg[l]));
+      double* Gd = reinterpret_cast<double*>(base + G.chol_scratch);
+      gin_gram64_kernel<<<dim3(ceil_div(H + 1, 16), ceil_div(H + 1, 16)), 256, 0, s>>>(bf(G.mlp0_w[l]), reinterpret_cast<const float*>(base + G.mlp0_b[l]),
+                                                                                      4 * H, H, Gd);
+      LLB_CUDA_OK(cudaGetLastError());
+      const int n1 = H + 1;
+      std::vector<double> Gh((size_t)n1 * n1), Lh;
+      LLB_CUDA_OK(cudaMemcpyAsync(Gh.data(), Gd, Gh.size() * 8, cudaMemcpyDeviceToHost, s));
+      LLB_CUDA_OK(cudaStreamSynchronize(s));
+      cholesky_lower_host(Gh, n1, Lh);
+      // R[k][i] = L[i][k] (upper factor, k = output row of the statistics GEMM's weight), r[k] = L[H][k], c0 = L[H][H]^2
+      std::vector<__nv_bfloat16> Rb((size_t)H * H);
+      std::vector<float> st(H + 4, 0.f);
+      for (int k = 0; k < H; ++k) {
+        for (int i = 0; i < H; ++i) Rb[(size_t)k * H + i] = __float2bfloat16(i >= k ? (float)Lh[(size_t)i * n1 + k] : 0.f);
+        st[k] = (float)Lh[(size_t)H * n1 + k];
+      }
+      st[H] = (float)(Lh[(size_t)H * n1 + H] * Lh[(size_t)H * n1 + H]);
+      LLB_CUDA_OK(cudaMemcpyAsync(base + G.mlp_chol[l], Rb.data(), Rb.size() * 2, cudaMemcpyHostToDevice, s));
+      LLB_CUDA_OK(cudaMemcpyAsync(base + G.mlp_stat[l], st.data(), st.size() * 4, cudaMemcpyHostToDevice, s));
+      LLB_CUDA_OK(cudaStreamSynchronize(s));   // Rb / st die with this scope
+    }
     LLB_CUDA_OK(cp(G.bond_emb[l], w->bond_emb[l], (size_t)BOND_VOCAB * H));
     if (!G.predictor) {
       LLB_CHECK_ARG(w->norm_w && w->norm_b, "gin: the encoder needs norms.{l}.weight/bias");
@@ -1001,6 +1066,14 @@ int llb_gin_create(const llb_gin_config* cfg, const void* packed, size_t packed_
     return st;
   }
   g->blob = (const uint8_t*)packed;
+  g->chol_c0.resize(g->G.L);
+  for (int l = 0; l < g->G.L; ++l) {   // synchronous: create is not on the hot path
+    cudaError_t e = cudaMemcpy(&g->chol_c0[l], g->blob + g->G.mlp_stat[l] + (size_t)g->G.H * 4, 4, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) {
+      delete g;
+      return fail(LLB_ERR_CUDA, "gin: reading the packed statistics back failed: %s", cudaGetErrorString(e));
+    }
+  }
   *out = g;
   return LLB_OK;
 }

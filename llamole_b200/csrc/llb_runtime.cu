@@ -255,7 +255,7 @@ const char* llb_profile_slot_name(int slot) {
   static const char* names[LLB_PROF_SLOTS] = {
       "gemm_qkv", "gemm_proj", "gemm_fc1", "gemm_fc2", "gemm_adaln", "gemm_other", "attention", "ln_mod_res", "dit_step",
       "dit_misc", "gin_aggregate", "gin_pool", "gin_gemm_mlp0", "gin_gemm_mlp4", "gin_rowln", "gin_misc", "gin_gemm_head",
-      "gin_topk"};
+      "gin_topk", "gin_gemm_stats"};
   return (slot >= 0 && slot < LLB_PROF_SLOTS) ? names[slot] : "?";
 }
 

@@ -179,9 +179,12 @@ class GraphDiT(nn.Module):
         raise ImportError("check_valid needs the reference's RDKit helpers (graph_decoder/molecule_utils.py)")
 
     def forward(self, x, edge_index, edge_attr, graph_batch, properties, text_embedding, no_label_index):
-        raise NotImplementedError(
-            "GraphDiT.forward is the SFT training loss (diffusion_model.py:148-250); the B200 path accelerates sampling only "
-            "(SURVEY.md section 8f-4) -- train with the reference module and load the weights here")
+        """SFT training loss (diffusion_model.py:148-172; called by modeling_llamole.py:371-379).  NOT accelerated: eager
+        PyTorch (llamole_b200/dit_train.py), differentiable, on the module's own device; same value as the reference for the
+        same torch.manual_seed.  The B200 kernels serve `generate` only."""
+        from .dit_train import graphdit_loss
+
+        return graphdit_loss(self, x, edge_index, edge_attr, graph_batch, properties, text_embedding, no_label_index)
 
     @torch.no_grad()
     def generate(self, properties, text_embedding, no_label_index) -> List[Optional[str]]:

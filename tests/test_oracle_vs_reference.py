@@ -83,3 +83,36 @@ def test_oracle_gin_matches_reference_on_fresh_inputs():
         assert torch.allclose(O.gin_encoder_forward(enc, proj, L, x, ei, ea, b), clip.eval()(x, ei, ea, b), atol=1e-6)
         assert torch.allclose(O.gin_predictor_forward(pred_sd, L, x, ei, ea, b, c), pred.eval()(x, ei, ea, b, c), atol=1e-4)
         assert torch.allclose(O.gin_predictor_forward(pred_sd, L, x, ei, ea, b, None), pred(x, ei, ea, b, None), atol=1e-4)
+
+
+@pytest.mark.parametrize("train", [False, True])
+def test_graphdit_forward_loss_matches_reference(train):
+    """GraphDiT.forward (the SFT loss, diffusion_model.py:148-250 + TrainLossDiscrete) of the drop-in class against the
+    verbatim reference module under the same torch.manual_seed: same timestep / noise / condition-dropout draws, hence the
+    same scalar (fp32 round-off) and the same gradients."""
+    cfg, meta = synth.dit_config(128, 2, 2, 4.0, 20, 2.0), synth.dit_meta(12, 3, 1)
+    sd = synth.dit_state_dict(cfg, 12, seed=8)
+    ref, d = _ref_dit(cfg, meta, sd)
+    mine = GraphDiT(os.path.join(d, "config.yaml"), os.path.join(d, "data.meta.json"), torch.float32)
+    mine.init_model(d)
+    ref.train(train), mine.train(train)
+    x, ei, ea, b = synth.molecular_graphs(5, seed=4, min_nodes=1, max_nodes=12)
+    active = (torch.tensor(meta["atom_type_dist"]) > 0).nonzero().squeeze()
+    x = active[x % 16]
+    x[3] = int((torch.tensor(meta["atom_type_dist"]) == 0).nonzero()[0])     # an atom outside the active set
+    props, txt = synth.dit_conditions(5, seed=2)
+    txt = txt.clone().requires_grad_(True)
+    txt_r = txt.detach().clone().requires_grad_(True)
+    for seed in (0, 1):
+        torch.manual_seed(seed)
+        want = ref(x, ei, ea, b, props, txt_r, -200)
+        torch.manual_seed(seed)
+        got = mine(x, ei, ea, b, props, txt, -200)
+        assert got.shape == want.shape == () and torch.allclose(got, want, rtol=1e-5, atol=1e-6), (float(got), float(want))
+    want.backward()
+    got.backward()
+    assert torch.allclose(txt.grad, txt_r.grad, rtol=1e-4, atol=1e-7)
+    gr = dict(ref.denoiser.named_parameters())
+    for k, p in mine.denoiser.named_parameters():
+        if gr[k].grad is not None:
+            assert p.grad is not None and torch.allclose(p.grad, gr[k].grad, rtol=2e-4, atol=1e-6), k
