@@ -76,6 +76,12 @@ template <class E, class = void>
 struct epi_row_state : std::false_type {};
 template <class E>
 struct epi_row_state<E, std::void_t<typename E::RowState>> : std::true_type {};
+// Functors that produce their 16-bit output already PACKED (half2 arithmetic) declare `static constexpr bool PACKS_OUTPUT = true`
+// and implement transform_pack(row, col0, const float* v, uint32_t* out16, M, N[, RowState&]): 32 accumulators -> 16 words.
+template <class E, class = void>
+struct epi_packs : std::false_type {};
+template <class E>
+struct epi_packs<E, std::void_t<decltype(E::PACKS_OUTPUT)>> : std::integral_constant<bool, E::PACKS_OUTPUT> {};
 struct EpiNoRowState {};
 template <class E, bool HAS = epi_row_state<E>::value>
 struct epi_row_state_of { using type = EpiNoRowState; };
@@ -84,9 +90,20 @@ struct epi_row_state_of<E, true> { using type = typename E::RowState; };
 
 // One epilogue warp's share of a 128 x BN accumulator tile: warp % 4 selects the TMEM lane quarter (32 rows), the
 // warps sharing a quarter split the columns.  tcgen05.ld -> fused functor -> swizzled smem staging -> TMA store.
+// The per-row state of this thread's row of tile row-block m0: computed BEFORE the thread waits for the tile's accumulators, so
+// that whatever the functor looks up for the row (e.g. its LayerNorm statistics) travels while the tile's MMAs still run.
+template <class Epi>
+__device__ __forceinline__ typename epi_row_state_of<Epi>::type gemm_epilogue_row_begin(const Epi& epi, int m0, int M) {
+  if constexpr (epi_row_state<Epi>::value) {
+    return epi.row_begin(m0 + (uniform_warp_idx() & 3) * 32 + (int)(threadIdx.x & 31), M);
+  } else {
+    return EpiNoRowState{};
+  }
+}
+
 template <int BN, bool TMA_STORE, class Epi>
 __device__ __forceinline__ void gemm_epilogue_tile(const Epi& epi, const CUtensorMap* tmC, uint32_t tmem_acc, int m0, int n0, int M,
-                                                   int N, uint8_t* stg, int& buf) {
+                                                   int N, uint8_t* stg, int& buf, typename epi_row_state_of<Epi>::type rst) {
   constexpr int ELEM = Epi::OUT_F32 ? 4 : 2;
   constexpr int ROW_BYTES = Epi::CHUNK * ELEM;
   constexpr int NBUF = GEMM_STAGING_PER_WARP / (32 * ROW_BYTES);
@@ -96,9 +113,10 @@ __device__ __forceinline__ void gemm_epilogue_tile(const Epi& epi, const CUtenso
   const int quarter = warp & 3, cg = warp >> 2;
   const int row = m0 + quarter * 32 + lane;
   const uint32_t t_row = tmem_acc + ((uint32_t)(quarter * 32) << 16) + cg * COLS_PER_WARP;
+  constexpr bool PACKS = epi_packs<Epi>::value;
+  static_assert(!PACKS || (!Epi::OUT_F32 && Epi::CHUNK == 32), "packed epilogues produce 32 16-bit columns per call");
   float v[Epi::CHUNK];
-  typename epi_row_state_of<Epi>::type rst;
-  if constexpr (ROW_STATE) rst = epi.row_begin(row, M);
+  [[maybe_unused]] uint32_t packed[PACKS ? 16 : 1];
 #pragma unroll 1
   for (int c = 0; c < COLS_PER_WARP; c += Epi::CHUNK) {
     const int col0 = n0 + cg * COLS_PER_WARP + c;
@@ -107,8 +125,14 @@ __device__ __forceinline__ void gemm_epilogue_tile(const Epi& epi, const CUtenso
     if (Epi::CHUNK == 64) tmem_ld32(t_row + c + 32, v + 32);
     tmem_ld_wait();
     if (!LLB_EXP(4)) {
-      if constexpr (ROW_STATE) epi.transform(row, col0, v, M, N, rst);
-      else epi.transform(row, col0, v, M, N);
+      if constexpr (PACKS) {
+        if constexpr (ROW_STATE) epi.transform_pack(row, col0, v, packed, M, N, rst);
+        else epi.transform_pack(row, col0, v, packed, M, N);
+      } else if constexpr (ROW_STATE) {
+        epi.transform(row, col0, v, M, N, rst);
+      } else {
+        epi.transform(row, col0, v, M, N);
+      }
     }
     if (LLB_EXP(8) || epi_no_store<Epi>::value) continue;
     if (TMA_STORE) {
@@ -121,7 +145,9 @@ __device__ __forceinline__ void gemm_epilogue_tile(const Epi& epi, const CUtenso
 #pragma unroll
       for (int p = 0; p < ROW_BYTES / 16; ++p) {
         uint4 q;
-        if (Epi::OUT_F32) {
+        if constexpr (PACKS) {
+          q = make_uint4(packed[4 * p], packed[4 * p + 1], packed[4 * p + 2], packed[4 * p + 3]);
+        } else if (Epi::OUT_F32) {
           q = make_uint4(__float_as_uint(v[4 * p]), __float_as_uint(v[4 * p + 1]), __float_as_uint(v[4 * p + 2]),
                          __float_as_uint(v[4 * p + 3]));
         } else {
@@ -138,7 +164,11 @@ __device__ __forceinline__ void gemm_epilogue_tile(const Epi& epi, const CUtenso
       }
       buf = (buf + 1) % NBUF;
     } else if (row < M) {
-      if (Epi::OUT_F32) {
+      if constexpr (PACKS) {   // unaligned C: pairs of 16-bit values through generic stores (ldc and N even)
+        uint32_t* out = reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(epi.C) + (size_t)row * epi.ldc + col0);
+        for (int i = 0; i < 16; ++i)
+          if (col0 + 2 * i < N) out[i] = packed[i];
+      } else if (Epi::OUT_F32) {
         float* out = reinterpret_cast<float*>(epi.C) + (size_t)row * epi.ldc + col0;
         for (int i = 0; i < Epi::CHUNK; ++i)
           if (col0 + i < N) out[i] = v[i];
@@ -160,11 +190,11 @@ __device__ __forceinline__ void gemm_epilogue_tile(const Epi& epi, const CUtenso
 //   __device__ void transform(int row, int col0, float* v, int M, int N) const   -- in place on v[CHUNK];
 //     called for every row of the tile, including rows >= M (their results are never stored).
 //   optional per-row state (struct RowState): RowState row_begin(row, M); transform(..., RowState&); row_end(row, slot, RowState&, M)
-//     -- row_begin once per (tile, thread) before the first chunk, row_end after the last one, slot as computed above.
+//     -- row_begin once per (tile, thread) BEFORE the thread waits for the accumulators, row_end after the last chunk, slot as above.
 template <int BN, bool TMA_STORE, class Epi>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmC, int M, int N, int K, Epi epi, int group_n, int group_k, int group_w) {
+                    const __grid_constant__ CUtensorMap tmC, int M, int N, int K, Epi epi, int group_n, int group_k, int group_w, int ab_f16) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int ELEM = Epi::OUT_F32 ? 4 : 2;
@@ -237,7 +267,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == GEMM_EPI_WARPS + 1) {
     // ---------------- MMA issuer: converged warp, one elected lane issues (operands stay in uniform registers) ----------------
-    constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
+    const uint32_t idesc = umma_idesc_ab(GEMM_BM, BN, ab_f16 != 0);
     const uint64_t a_desc0 = umma_desc_k128(smem_u32(smA));   // stage 0, k-step 0; stages / k-steps are plain adds
     const uint64_t b_desc0 = umma_desc_k128(smem_u32(smB));
     int stage = 0;
@@ -280,9 +310,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / num_n) * GEMM_BM;
       const int n0 = (tile % num_n) * BN;
+      const auto rst = gemm_epilogue_row_begin(epi, m0, M);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      gemm_epilogue_tile<BN, TMA_STORE>(epi, &tmC, tmem_base + acc * BN, m0, n0, M, N, stg, buf);
+      gemm_epilogue_tile<BN, TMA_STORE>(epi, &tmC, tmem_base + acc * BN, m0, n0, M, N, stg, buf, rst);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -363,7 +394,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
 template <bool TMA_STORE, class Epi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const __grid_constant__ CUtensorMap tmC, int M, int N, int K, Epi epi, int group_n, int group_k, int group_w) {
+                         const __grid_constant__ CUtensorMap tmC, int M, int N, int K, Epi epi, int group_n, int group_k, int group_w, int ab_f16) {
   using Cfg = Gemm2Cfg;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int BN = Cfg::BN;
@@ -451,7 +482,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   } else if (warp == GEMM_EPI_WARPS + 1) {
     // ---------------- MMA issuer (leader CTA only): converged warp, one elected lane issues ----------------
     if (rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(2 * GEMM_BM, BN);
+      const uint32_t idesc = umma_idesc_ab(2 * GEMM_BM, BN, ab_f16 != 0);
       const uint64_t a_desc0 = umma_desc_k128(smem_u32(smA));   // stage 0, k-step 0; stages / k-steps are plain adds
       const uint64_t b_desc0 = umma_desc_k128(smem_u32(smB));
       int stage = 0;
@@ -511,10 +542,11 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const int m0 = (tile / num_n) * (2 * GEMM_BM) + rank * GEMM_BM;
       const int n0 = (tile % num_n) * BN;
       if (warp == 0 && lane == 0) LLB_TRACE(tcount, 6, clock64());
+      const auto rst = gemm_epilogue_row_begin(epi, m0, M);
       mbar_wait(&tmem_full[acc], acc_phase);
       if (warp == 0 && lane == 0) LLB_TRACE(tcount, 7, clock64());
       tc_fence_after();
-      if (!LLB_EXP(2)) gemm_epilogue_tile<BN, TMA_STORE>(epi, &tmC, tmem_base + acc * BN, m0, n0, M, N, stg, buf);
+      if (!LLB_EXP(2)) gemm_epilogue_tile<BN, TMA_STORE>(epi, &tmC, tmem_base + acc * BN, m0, n0, M, N, stg, buf, rst);
       tc_fence_before();
       __syncwarp();
       if (warp == 0 && lane == 0) LLB_TRACE(tcount, 8, clock64());
@@ -552,6 +584,7 @@ bool gemm_pair_enabled();   // LLB_GEMM_PAIR=0 forces the single-CTA kernel (deb
 struct GemmGroups {
   int group_n = 0, group_k = 0;
   bool split_k = false;
+  bool ab_f16 = false;   // both operands are IEEE fp16 instead of bf16 (same tile shapes, same descriptors otherwise)
 };
 
 struct GemmCounters {
@@ -596,7 +629,7 @@ int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, in
       }
       const int pairs = pair_tiles < num_sms() / 2 ? pair_tiles : num_sms() / 2;
       ProfScope prof(ctr ? ctr->slot : LLB_PROF_GEMM_OTHER, stream);
-      kern<<<2 * pairs, GEMM_THREADS, Gemm2Cfg::SMEM_BYTES, stream>>>(tmA, tmBh, tmC, M, N, K, epi, grp.group_n, grp.group_k, grp.split_k ? 1 : 0);
+      kern<<<2 * pairs, GEMM_THREADS, Gemm2Cfg::SMEM_BYTES, stream>>>(tmA, tmBh, tmC, M, N, K, epi, grp.group_n, grp.group_k, grp.split_k ? 1 : 0, grp.ab_f16 ? 1 : 0);
       note_kernel(LLB_KERN_GEMM_2CTA);
       return LLB_OK;
     };
@@ -609,7 +642,7 @@ int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, in
         configured[which] = true;
       }
       ProfScope prof(ctr ? ctr->slot : LLB_PROF_GEMM_OTHER, stream);
-      kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, M, N, K, epi, grp.group_n, grp.group_k, grp.split_k ? 1 : 0);
+      kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, M, N, K, epi, grp.group_n, grp.group_k, grp.split_k ? 1 : 0, grp.ab_f16 ? 1 : 0);
       note_kernel(LLB_KERN_GEMM_1CTA);
       return LLB_OK;
     };

@@ -294,6 +294,129 @@ __device__ __forceinline__ void gln_pass2_tma(const GlnPass2& a, const CUtensorM
 #endif
 }
 
+// Pass 2 of the GIN layer tail (GinTailArgs): same data path as gln_pass2_tma -- the residual chunk arrives by TMA in the warp's
+// staging tile, thread = row adds its 32 values in place, the tile goes back by TMA -- with the GIN arithmetic in between.  The
+// per-graph vectors (text-adaLN shift / scale / gate, next virtual node) are read straight from global memory: the 32 rows of a
+// warp belong to a handful of graphs, so these are mostly same-address loads, and with K = 4 H the epilogue has ~12k cycles.
+struct GinRow {
+  const float* sc;   // scale row of this thread's graph at the warp's first column (null: affine gamma / beta from shared memory)
+  const float* sh;
+  const float* gt;   // gate row or null
+  const float* av;   // addvec row or null
+  uint32_t gamma_s, beta_s;   // shared addresses at the warp's first column
+  int group;         // graph of this thread's row
+  int nvalid;        // rows of this warp's 32 that exist (row < M): 0..32, warp-uniform
+  uint32_t heads;    // bit r: row r of the warp starts a new graph (bit 0 unused), warp-uniform
+};
+template <int NXB>
+__device__ __forceinline__ void gin_pass2_tma(const GlnPass2& a, const GinRow& gr, const GinTailArgs& t, const CUtensorMap* tmX,
+                                              const CUtensorMap* tmXb, uint64_t* res_full, uint32_t& res_phase, int lane) {
+  float v[32];
+#pragma unroll 1
+  for (int ci = 0; ci < GLN_BN / 2 / 32; ++ci) {
+    const int c = ci * 32;
+    const int b = NXB == 2 ? (ci & 1) : 0;
+    tmem_ld32(a.t_row + c, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      const float4 bb = lds128(a.bias_s + (c + 4 * p) * 4);
+      float4 s1, sh;
+      if (gr.sc != nullptr) {
+        s1 = __ldg(reinterpret_cast<const float4*>(gr.sc + c + 4 * p));
+        sh = __ldg(reinterpret_cast<const float4*>(gr.sh + c + 4 * p));
+        s1.x += 1.0f, s1.y += 1.0f, s1.z += 1.0f, s1.w += 1.0f;
+      } else {
+        s1 = lds128(gr.gamma_s + (c + 4 * p) * 4);
+        sh = lds128(gr.beta_s + (c + 4 * p) * 4);
+      }
+      float x0 = fmaf(fmaf(v[4 * p] + bb.x, a.rstd, a.nmr), s1.x, sh.x);
+      float x1 = fmaf(fmaf(v[4 * p + 1] + bb.y, a.rstd, a.nmr), s1.y, sh.y);
+      float x2 = fmaf(fmaf(v[4 * p + 2] + bb.z, a.rstd, a.nmr), s1.z, sh.z);
+      float x3 = fmaf(fmaf(v[4 * p + 3] + bb.w, a.rstd, a.nmr), s1.w, sh.w);
+      if (t.act == LLB_ACT_GELU) x0 = gelu_fast(x0), x1 = gelu_fast(x1), x2 = gelu_fast(x2), x3 = gelu_fast(x3);
+      if (gr.gt != nullptr) {
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gr.gt + c + 4 * p));
+        x0 *= g4.x, x1 *= g4.y, x2 *= g4.z, x3 *= g4.w;
+      }
+      if (gr.av != nullptr) {
+        const float4 a4 = __ldg(reinterpret_cast<const float4*>(gr.av + c + 4 * p));
+        x0 += a4.x, x1 += a4.y, x2 += a4.z, x3 += a4.w;
+      }
+      v[4 * p] = x0, v[4 * p + 1] = x1, v[4 * p + 2] = x2, v[4 * p + 3] = x3;
+    }
+    // the previous chunk's stores have read their staging tiles: the bf16 tile and the other fp32 tile are free
+    if (elect_one()) {
+      bulk_wait_read<0>();
+      if (NXB == 2 && ci + 1 < GLN_BN / 2 / 32) {
+        mbar_arrive_expect_tx(&res_full[b ^ 1], 4096);
+        tma_load_2d(reinterpret_cast<void*>(__cvta_shared_to_generic(a.xstg + (b ^ 1) * 4096)), tmX, &res_full[b ^ 1], a.gcol + c + 32, a.grow);
+      }
+    }
+    __syncwarp();
+    mbar_wait(&res_full[b], (res_phase >> b) & 1u);
+    res_phase ^= 1u << b;
+    const uint32_t xs = a.xstg + b * 4096 + lane * 128;
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      const uint32_t addr = xs + ((p ^ (lane & 7)) << 4);
+      const float4 r = lds128(addr);
+      v[4 * p] += r.x, v[4 * p + 1] += r.y, v[4 * p + 2] += r.z, v[4 * p + 3] += r.w;
+      sts128(addr, make_float4(v[4 * p], v[4 * p + 1], v[4 * p + 2], v[4 * p + 3]));
+    }
+    const uint32_t xbs = a.xbstg + lane * 64;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float4 q;
+      q.x = __uint_as_float(pack_bf16x2(v[8 * j], v[8 * j + 1])), q.y = __uint_as_float(pack_bf16x2(v[8 * j + 2], v[8 * j + 3]));
+      q.z = __uint_as_float(pack_bf16x2(v[8 * j + 4], v[8 * j + 5])), q.w = __uint_as_float(pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+      sts128(xbs + ((j ^ ((lane >> 1) & 3)) << 4), q);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (elect_one()) {
+      tma_store_2d(tmX, reinterpret_cast<const void*>(__cvta_shared_to_generic(a.xstg + b * 4096)), a.gcol + c, a.grow);
+      tma_store_2d(tmXb, reinterpret_cast<const void*>(__cvta_shared_to_generic(a.xbstg)), a.gcol + c, a.grow);
+      bulk_commit();
+    }
+    if (t.pool_max != nullptr && gr.nvalid > 0) {
+      // per-graph column maxima of the new rows: lane = column of the chunk, reading the warp's 32 rows back from the staging
+      // tile (the swizzle spreads a row's 32 columns over the 32 banks: conflict-free).  The rows' graph boundaries are a
+      // tile-constant bit mask, so the scan is 32 independent loads and a chain of uniform selects; every run of equal graph ids
+      // ends in ONE 128-byte atomicMax (order-independent, hence deterministic).
+      const uint32_t xt = a.xstg + b * 4096;
+      const int cq = lane >> 2, cw = lane & 3;
+      float vals[32];
+#pragma unroll
+      for (int r = 0; r < 32; ++r)
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(vals[r]) : "r"(xt + r * 128 + ((cq ^ (r & 7)) << 4) + cw * 4));
+      uint32_t* pcol = t.pool_max + a.gcol + c + lane;
+      float run = vals[0];
+#pragma unroll
+      for (int r = 1; r < 32; ++r) {
+        if (r < gr.nvalid) {                 // warp-uniform
+          if ((gr.heads >> r) & 1u) {        // warp-uniform: row r starts a new graph -> flush the finished one
+            atomicMax(pcol + (size_t)__shfl_sync(0xffffffffu, gr.group, r - 1) * t.pool_ld, float_order_enc(__float_as_uint(run)));
+            run = vals[r];
+          } else {
+            run = fmaxf(run, vals[r]);
+          }
+        }
+      }
+      atomicMax(pcol + (size_t)__shfl_sync(0xffffffffu, gr.group, gr.nvalid - 1) * t.pool_ld, float_order_enc(__float_as_uint(run)));
+      __syncwarp();
+    }
+    if (NXB == 1 && ci + 1 < GLN_BN / 2 / 32) {   // single tile: reload it as soon as the store has read it
+      if (elect_one()) {
+        bulk_wait_read<0>();
+        mbar_arrive_expect_tx(&res_full[0], 4096);
+        tma_load_2d(reinterpret_cast<void*>(__cvta_shared_to_generic(a.xstg)), tmX, &res_full[0], a.gcol + c + 32, a.grow);
+      }
+      __syncwarp();
+    }
+  }
+}
+
 // Modulation stager, one warp, one tile: which modulation rows do the tile's 128 token rows use (runs of equal
 // row_group), stage gate*(1+scale) and gate*shift of those rows (this CTA's 256 columns) in shared memory, and pull the
 // CTA's block of the residual stream into L2 for the epilogue's pass 2.
@@ -674,18 +797,28 @@ __device__ __forceinline__ uint4 ld_mailbox(const uint4* p) {
   return v;
 }
 
-template <int STAGES_, int MODST_, int NXB_>
+// Epilogue payload of the pair kernel: the GraphDiT block tail (GemmLnArgs) or the GIN layer tail (GinTailArgs).
+template <bool GIN>
+struct PairTail {
+  using type = GemmLnArgs;
+};
+template <>
+struct PairTail<true> {
+  using type = GinTailArgs;
+};
+
+template <int STAGES_, int MODST_, int NXB_, int NS, bool GIN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
                     const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXb,
-                    const __grid_constant__ CUtensorMap tmXpf, int M, int K, int G, GemmLnArgs e, uint4* sync_stats,
+                    const __grid_constant__ CUtensorMap tmXpf, int M, int K, int G, typename PairTail<GIN>::type e, uint4* sync_stats,
                     uint32_t tag_base, int prefetch_x) {
   using S = GlnPairSmemT<STAGES_, MODST_, NXB_>;
   constexpr int STAGES = S::STAGES;
   constexpr int MODST = S::MODST;
   constexpr int NXB = S::NXB;
   constexpr int BN = GLN_BN;
-  constexpr int NS = 4;   // column slices of 256 = pairs per group
+  // NS column slices of 256 = pairs per group
   const uint32_t rank = cluster_rank();
   const int pair = blockIdx.x >> 1;
   const int grp = pair / NS, slice = pair % NS;
@@ -737,7 +870,13 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int a = 0; a < 2 * GEMM_EPI_WARPS; ++a) mbar_init(&res_full[a], 1);
     fence_mbar_init();
   }
-  if (threadIdx.x < BN) biasS[threadIdx.x] = e.bias ? e.bias[n0 + threadIdx.x] : 0.0f;
+  if (threadIdx.x < BN) {
+    biasS[threadIdx.x] = e.bias ? e.bias[n0 + threadIdx.x] : 0.0f;
+    if constexpr (GIN) {   // affine LayerNorm weight / bias of this CTA's columns live where the DiT variant stages its modulations
+      modS[threadIdx.x] = e.gamma ? e.gamma[n0 + threadIdx.x] : 1.0f;
+      modS[BN + threadIdx.x] = e.beta ? e.beta[n0 + threadIdx.x] : 0.0f;
+    }
+  }
   cluster_sync_all();
   if (warp == GEMM_EPI_WARPS + 2) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(2 * BN))
@@ -773,7 +912,7 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp == GEMM_EPI_WARPS + 1) {
     // ---------------- MMA issuer (leader CTA only; converged warp, one elected lane issues) ----------------
     if (rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(2 * GEMM_BM, BN);
+      const uint32_t idesc = umma_idesc_ab(2 * GEMM_BM, BN, GIN && (prefetch_x & 2) != 0);   // GIN tail: bit 1 = fp16 operands
       const uint64_t a_desc0 = umma_desc_k128(smem_u32(smA));
       const uint64_t b_desc0 = umma_desc_k128(smem_u32(smB));
       int stage = 0;
@@ -813,18 +952,20 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else if (warp == GEMM_EPI_WARPS + 3) {
-    // ---------------- modulation stager ----------------
-    int st = 0;
-    uint32_t ph = 0;
-    for (int mb = grp; mb < num_mb; mb += G) {
-      const int m0 = mb * 2 * GEMM_BM + (int)rank * GEMM_BM;
-      mbar_wait(&mod_empty[st], ph ^ 1);
-      gln_stage_tile(e, prefetch_x ? &tmXpf : nullptr, modS + (size_t)st * S::MOD_STAGE_FLOATS, rowinfoS + st * GEMM_BM, glistS + st * 8, m0, n0, M,
-                     lane);
-      if (lane == 0) mbar_arrive(&mod_full[st]);
-      if (++st == MODST) {
-        st = 0;
-        ph ^= 1;
+    // ---------------- modulation stager (GraphDiT tail only) ----------------
+    if constexpr (!GIN) {
+      int st = 0;
+      uint32_t ph = 0;
+      for (int mb = grp; mb < num_mb; mb += G) {
+        const int m0 = mb * 2 * GEMM_BM + (int)rank * GEMM_BM;
+        mbar_wait(&mod_empty[st], ph ^ 1);
+        gln_stage_tile(e, prefetch_x ? &tmXpf : nullptr, modS + (size_t)st * S::MOD_STAGE_FLOATS, rowinfoS + st * GEMM_BM, glistS + st * 8, m0, n0, M,
+                       lane);
+        if (lane == 0) mbar_arrive(&mod_full[st]);
+        if (++st == MODST) {
+          st = 0;
+          ph ^= 1;
+        }
       }
     }
   } else if (warp < GEMM_EPI_WARPS) {
@@ -848,6 +989,10 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int mb = grp; mb < num_mb; mb += G, ++tcount) {
       const int m0 = mb * 2 * GEMM_BM + (int)rank * GEMM_BM;
       if (tr) GLN_TRACE(tcount, 0, clock64());
+      if constexpr (GIN) {   // pull the NEXT tile's block of the node features into L2 while this tile is being finished
+        const int m0n = m0 + G * 2 * GEMM_BM;
+        if ((prefetch_x & 1) && warp == 0 && lane == 0 && m0n < M) l2_prefetch_tile(&tmXpf, n0, m0n);
+      }
       // the tile's first residual chunk starts its way into the staging tile now (the previous tile's stores have read it)
       a.grow = m0 + q * 32;
       if (elect_one()) {
@@ -861,7 +1006,7 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (tr) GLN_TRACE(tcount, 2, clock64());
       tc_fence_after();
       a.t_row = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16) + cbase;
-      if (GLN_EXP(16)) {   // knock-out: empty epilogue (main loop alone)
+      if (!GIN && GLN_EXP(16)) {   // knock-out: empty epilogue (main loop alone)
         mbar_wait(&res_full[warp * 2], res_phase & 1u);
         res_phase ^= 1u;
         mbar_wait(&mod_full[ms], mph);
@@ -896,7 +1041,7 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // the partial sums are kept per source and added in slice order once all four are in: adding them in ARRIVAL
         // order made the fp32 row statistics -- and through them a few sampled categories per step -- vary from run to run
         float sv[NS], ssv[NS];
-        uint32_t pending = 0xFu;
+        uint32_t pending = (1u << NS) - 1u;
         const long long start = clock64();
         while (pending) {
 #pragma unroll
@@ -924,27 +1069,45 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         a.nmr = -mean * a.rstd;
       }
       a.trace_tile = tr ? tcount : -1;
-      // the tile's modulation rows are staged (the stager had pass 1 and the exchange to do it)
-      mbar_wait(&mod_full[ms], mph);
-      const int2 info = rowinfoS[ms * GEMM_BM + rloc];
-      const bool staged = glistS[ms * 8 + 4] <= GLN_MAX_GROUPS;
-      if (GLN_EXP(8)) {
-        mbar_wait(&res_full[warp * 2], res_phase & 1u);
-        res_phase ^= 1u;
-      } else if (staged) {
-        a.mod_s = smem_u32(modS + (size_t)ms * S::MOD_STAGE_FLOATS + (size_t)info.x * 2 * BN + cbase);
-        gln_pass2_tma<true, NXB>(a, &tmX, &tmXb, &res_full[warp * 2], res_phase, lane);
+      if constexpr (GIN) {
+        const int row = m0 + rloc;
+        GinRow gr;
+        gr.group = __ldg(e.row_group + (row < M ? row : M - 1));
+        gr.nvalid = M - (m0 + q * 32) < 32 ? (M - (m0 + q * 32) > 0 ? M - (m0 + q * 32) : 0) : 32;
+        {
+          const int gup = __shfl_up_sync(0xffffffffu, gr.group, 1);
+          gr.heads = __ballot_sync(0xffffffffu, lane > 0 && gr.group != gup);
+        }
+        const size_t moff = (size_t)gr.group * e.mod_ld + n0 + cbase;
+        gr.sc = e.scale ? e.scale + moff : nullptr;
+        gr.sh = e.shift ? e.shift + moff : nullptr;
+        gr.gt = e.gate ? e.gate + moff : nullptr;
+        gr.av = e.addvec ? e.addvec + (size_t)gr.group * e.addvec_ld + n0 + cbase : nullptr;
+        gr.gamma_s = smem_u32(modS + cbase), gr.beta_s = smem_u32(modS + BN + cbase);
+        gin_pass2_tma<NXB>(a, gr, e, &tmX, &tmXb, &res_full[warp * 2], res_phase, lane);
       } else {
-        const size_t off = (size_t)info.y * e.mod_ld + n0 + cbase;
-        a.g_shift = e.shift + off, a.g_scale = e.scale + off, a.g_gate = e.gate + off;
-        gln_pass2_tma<false, NXB>(a, &tmX, &tmXb, &res_full[warp * 2], res_phase, lane);
+        // the tile's modulation rows are staged (the stager had pass 1 and the exchange to do it)
+        mbar_wait(&mod_full[ms], mph);
+        const int2 info = rowinfoS[ms * GEMM_BM + rloc];
+        const bool staged = glistS[ms * 8 + 4] <= GLN_MAX_GROUPS;
+        if (GLN_EXP(8)) {
+          mbar_wait(&res_full[warp * 2], res_phase & 1u);
+          res_phase ^= 1u;
+        } else if (staged) {
+          a.mod_s = smem_u32(modS + (size_t)ms * S::MOD_STAGE_FLOATS + (size_t)info.x * 2 * BN + cbase);
+          gln_pass2_tma<true, NXB>(a, &tmX, &tmXb, &res_full[warp * 2], res_phase, lane);
+        } else {
+          const size_t off = (size_t)info.y * e.mod_ld + n0 + cbase;
+          a.g_shift = e.shift + off, a.g_scale = e.scale + off, a.g_gate = e.gate + off;
+          gln_pass2_tma<false, NXB>(a, &tmX, &tmXb, &res_full[warp * 2], res_phase, lane);
+        }
       }
       if (tr) GLN_TRACE(tcount, 5, clock64());
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         mbar_arrive_cluster(&tmem_empty[acc], 0);
-        mbar_arrive(&mod_empty[ms]);
+        if (!GIN) mbar_arrive(&mod_empty[ms]);
       }
       if (++acc == 2) {
         acc = 0;
@@ -1060,7 +1223,7 @@ int launch_gemm_ln_pair(const void* A, int lda, const void* W, int ldw, int M, i
   // 128 KB TMA prefetch per tile delays the ring's loads; the residual reads hide behind the MMAs anyway);
   // short K: the epilogue is -> modulation stager two tiles ahead, residual prefetched.
   const bool long_k = K > 2048;
-  auto kern = long_k ? gemm_ln_pair_kernel<5, 1, 1> : gemm_ln_pair_kernel<4, 1, 2>;
+  auto kern = long_k ? gemm_ln_pair_kernel<5, 1, 1, 4, false> : gemm_ln_pair_kernel<4, 1, 2, 4, false>;
   const int smem_bytes = long_k ? GlnPairSmemT<5, 1, 1>::TOTAL : GlnPairSmemT<4, 1, 2>::TOTAL;
   static bool configured[2] = {false, false};
   static int max_groups_v[2] = {0, 0};
@@ -1111,6 +1274,90 @@ int launch_gemm_ln_pair(const void* A, int lda, const void* W, int ldw, int M, i
   LLB_CUDA_OK(cudaGetLastError());
   if (ctr) ctr->launches++;
   return LLB_OK;
+}
+
+template <int NS>
+static int launch_gin_tail_ns(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const GinTailArgs& t, void* sync_ws,
+                              cudaStream_t stream, GemmCounters* ctr) {
+  CUtensorMap tmA, tmBh, tmX, tmXb, tmXpf;
+  LLB_TRY(make_tensor_map_2d(&tmA, A, 2, M, K, lda, GEMM_BK, GEMM_BM, 128));
+  LLB_TRY(make_tensor_map_2d(&tmBh, W, 2, N, K, ldw, GEMM_BK, GLN_BN / 2, 128));
+  LLB_TRY(make_tensor_map_2d(&tmX, t.x, 4, M, N, t.ldx, 32, 32, 128));
+  LLB_TRY(make_tensor_map_2d(&tmXb, t.xb, 2, M, N, t.ldxb, 32, 32, 64));
+  LLB_TRY(make_tensor_map_2d(&tmXpf, t.x, 4, M, N, t.ldx, GLN_BN, GEMM_BM, 0));
+  // (5 stages, one staging tile) or (4 stages, two staging tiles: the next chunk's residual is loaded a chunk ahead)
+  static const int cfg_env = getenv("LLB_GIN_TAIL_CFG") ? atoi(getenv("LLB_GIN_TAIL_CFG")) : -1;
+  const bool long_k = cfg_env >= 0 ? (cfg_env & 1) == 0 : K > 2048;
+  const int prefetch_x = (cfg_env >= 0 ? (cfg_env >> 1) & 1 : 0) | (t.a_f16 ? 2 : 0);
+  auto kern = long_k ? gemm_ln_pair_kernel<5, 1, 1, NS, true> : gemm_ln_pair_kernel<4, 1, 2, NS, true>;
+  const int smem_bytes = long_k ? GlnPairSmemT<5, 1, 1>::TOTAL : GlnPairSmemT<4, 1, 2>::TOTAL;
+  static bool configured[2] = {false, false};
+  static int max_groups_v[2] = {0, 0};
+  static bool cooperative = true;
+  if (!configured[long_k]) {
+    LLB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    cudaLaunchConfig_t q = {};
+    q.blockDim = dim3(GEMM_THREADS), q.dynamicSmemBytes = smem_bytes, q.gridDim = dim3(2 * (num_sms() / 2));
+    int n = 0;
+    LLB_CUDA_OK(cudaOccupancyMaxActiveClusters(&n, kern, &q));
+    // the mailbox area holds GLN_PAIR_MAX_GROUPS x 4 slices = 72 (group, slice) columns
+    const int cap = GLN_PAIR_MAX_GROUPS * 4 / NS;
+    max_groups_v[long_k] = n / NS < cap ? n / NS : cap;
+    LLB_CHECK_ARG(max_groups_v[long_k] > 0, "gin_tail: fewer than %d CTA pairs fit on this device", NS);
+    configured[long_k] = true;
+  }
+  const int max_groups = max_groups_v[long_k];
+  const int num_mb = ceil_div(M, 2 * GEMM_BM);
+  const int G = num_mb < max_groups ? num_mb : max_groups;
+  uint4* stats = reinterpret_cast<uint4*>(sync_ws);
+  static std::atomic<uint32_t> epoch{0x9117};
+  LLB_CHECK_ARG(ceil_div(num_mb, G) < 4096, "gin_tail: M=%d is too large for the mailbox tags", M);
+  const uint32_t tag_base = epoch.fetch_add(1) << 12;
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;   // every CTA of the grid is resident: the pairs of a group spin on each other
+  attr[0].val.cooperative = 1;
+  cfg.blockDim = dim3(GEMM_THREADS), cfg.dynamicSmemBytes = smem_bytes, cfg.stream = stream, cfg.attrs = attr;
+  cfg.gridDim = dim3(2 * NS * G);
+  {
+    ProfScope prof(ctr ? ctr->slot : LLB_PROF_GEMM_OTHER, stream);
+    cudaError_t err = cudaErrorNotSupported;
+    if (cooperative) {
+      cfg.numAttrs = 1;
+      err = cudaLaunchKernelEx(&cfg, kern, tmA, tmBh, tmX, tmXb, tmXpf, M, K, G, t, stats, tag_base, prefetch_x);
+      if (err != cudaSuccess) {
+        (void)cudaGetLastError();
+        cooperative = false;
+      }
+    }
+    if (!cooperative) {
+      cfg.numAttrs = 0;
+      err = cudaLaunchKernelEx(&cfg, kern, tmA, tmBh, tmX, tmXb, tmXpf, M, K, G, t, stats, tag_base, prefetch_x);
+    }
+    LLB_CUDA_OK(err);
+    note_kernel(LLB_KERN_GIN_FUSED_MLP);
+  }
+  LLB_CUDA_OK(cudaGetLastError());
+  if (ctr) ctr->launches++;
+  return LLB_OK;
+}
+
+int launch_gin_tail(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const GinTailArgs& t, void* sync_ws, size_t sync_bytes,
+                    cudaStream_t stream, GemmCounters* ctr) {
+  if (M <= 0) return LLB_OK;
+  LLB_CHECK_ARG(gin_tail_supported(N, K), "gin_tail: N=%d must be 768 or 1024 and K=%d a multiple of 8", N, K);
+  LLB_CHECK_ARG(lda % 8 == 0 && ldw % 8 == 0 && t.ldx % 4 == 0 && t.ldxb % 8 == 0 && t.mod_ld % 4 == 0 && t.addvec_ld % 4 == 0,
+                "gin_tail: leading dimensions must keep rows 16-byte aligned");
+  LLB_CHECK_ARG(t.row_group && t.x && t.xb && ((t.gamma && t.beta) || (t.shift && t.scale)), "gin_tail: null operand");
+  LLB_CHECK_ARG(sync_ws && sync_bytes >= gemm_ln_pair_workspace_bytes() && (reinterpret_cast<uintptr_t>(sync_ws) & 127) == 0,
+                "gin_tail: the exchange workspace needs %zu bytes, 128-byte aligned", gemm_ln_pair_workspace_bytes());
+  LLB_CHECK_ARG(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(t.x) | reinterpret_cast<uintptr_t>(t.xb) |
+                  reinterpret_cast<uintptr_t>(t.shift) | reinterpret_cast<uintptr_t>(t.scale) | reinterpret_cast<uintptr_t>(t.gate) |
+                  reinterpret_cast<uintptr_t>(t.addvec)) & 15) == 0,
+                "gin_tail: operands must be 16-byte aligned");
+  LLB_CHECK_ARG(A != (const void*)t.xb, "gin_tail: the A operand must not alias the bf16 output");
+  if (N == 3 * GLN_BN) return launch_gin_tail_ns<3>(A, lda, W, ldw, M, N, K, t, sync_ws, stream, ctr);
+  return launch_gin_tail_ns<4>(A, lda, W, ldw, M, N, K, t, sync_ws, stream, ctr);
 }
 
 }  // namespace llb

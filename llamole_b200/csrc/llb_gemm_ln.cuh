@@ -51,6 +51,40 @@ inline bool gemm_ln_enabled() { return gemm_ln_mode() != 0; }
 int launch_gemm_ln(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const GemmLnArgs& e, cudaStream_t stream,
                    GemmCounters* ctr);
 
+// Tail of a GIN layer fused into the second linear of the node MLP (graph_encoder/model.py:131-149, graph_predictor/model.py:318-348):
+//   h[r,:] = gate_g * act( LN(A[r,:] . W^T + bias) * s1 + sh ) + h[r,:] + addvec_g      g = row_group[r] (graph of node r)
+// with (s1, sh) = (gamma, beta) per column (encoder: affine LayerNorm) or (1 + scale_g, shift_g) per graph (predictor: text-adaLN);
+// gate / addvec optional.  h (fp32, in place) and hb (its bf16 copy) are written through TMA; optionally the per-graph column
+// MAXIMUM of the new h is accumulated into pool_max (order-preserving uint encoding, atomicMax: order-independent, hence
+// deterministic) -- the next layer's virtual-node update pools exactly this matrix (model.py:148).
+struct GinTailArgs {
+  const float* bias;          // (N)
+  const int32_t* row_group;   // (M) graph id per node row, non-decreasing
+  const float* gamma;         // (N) or null
+  const float* beta;          // (N) or null
+  const float* shift;         // (graphs, mod_ld) or null
+  const float* scale;
+  const float* gate;
+  int mod_ld;
+  const float* addvec;        // (graphs, addvec_ld) or null
+  int addvec_ld;
+  int act;                    // LLB_ACT_NONE or LLB_ACT_GELU
+  float* x;                   // (M, ldx) fp32 node features, updated in place
+  int ldx;
+  __nv_bfloat16* xb;          // (M, ldxb)
+  int ldxb;
+  uint32_t* pool_max;         // (graphs, pool_ld) encoded running maxima (cleared to 0 by the caller) or null
+  int pool_ld;
+  int a_f16;                  // A and W are IEEE fp16 instead of bf16
+};
+// N = 768 (three CTA pairs per 256-row block) or 1024 (four); needs the same exchange workspace as launch_gemm_ln_pair.
+inline bool gin_tail_supported(int N, int K) { return (N == 3 * GLN_BN || N == 4 * GLN_BN) && K % 8 == 0; }
+int launch_gin_tail(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const GinTailArgs& t, void* sync_ws, size_t sync_bytes,
+                    cudaStream_t stream, GemmCounters* ctr);
+// order-preserving encoding of a float for unsigned atomicMax (0 = below every float)
+__host__ __device__ inline uint32_t float_order_enc(uint32_t bits) { return (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u); }
+__host__ __device__ inline uint32_t float_order_dec(uint32_t e) { return (e & 0x80000000u) ? (e & 0x7fffffffu) : ~e; }
+
 // CTA-pair variant for N = 1024 (see llb_gemm_ln.cu): needs a caller-provided exchange workspace (any contents; the launch
 // clears its counters with a stream-ordered memset) that no other launch uses concurrently.
 size_t gemm_ln_pair_workspace_bytes();

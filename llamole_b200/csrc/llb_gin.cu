@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "llb_gemm.cuh"
+#include "llb_gemm_ln.cuh"
 #include "llb_rowops.cuh"
 
 namespace llb {
@@ -364,40 +365,58 @@ struct EpiRowSq {
   }
 };
 
-// Epilogue of the first linear (centred weight) with the row's |zc|^2 known: GELU(zc * rstd * gamma + beta) -> bf16.
+// Epilogue of the first linear (centred weight) with the row's |zc|^2 known: GELU(zc * rstd * gamma + beta) -> fp16.
+// The affine part runs in fp32 on the accumulators; the GELU runs on PAIRS in fp16 (gelu_h2) and its result is stored as is:
+// the intermediate of the node MLP is an fp16 matrix (values of order one: three more mantissa bits than bf16), consumed by the
+// second linear with fp16 operands.  With K = H the epilogue of this GEMM, not its MMAs, sets the pace (ncu: tensor pipe 72 %
+// active with the fp32 GELU + bf16 pack); the row's partial sums are fetched before the thread waits for the accumulators.
 struct EpiLnGelu {
   static constexpr int CHUNK = 32;
   static constexpr bool OUT_F32 = false;
+  static constexpr bool PACKS_OUTPUT = true;
   void* C;
   int ldc;
   const float *gamma, *bgamma, *beta;   // (N): LayerNorm weight, centred bias x weight, LayerNorm bias
   const float* part;                    // (M, slots) from EpiRowSq
-  int slots;
+  int slots;                            // even
   float c0, inv_rows;                   // constant of the factor, 1 / 4H
   struct RowState {
     float rstd;
   };
   __device__ __forceinline__ RowState row_begin(int row, int M) const {
     float q = c0;
-    if (row < M)
-      for (int s = 0; s < slots; ++s) q += __ldg(part + (size_t)row * slots + s);   // slot order: deterministic
+    if (row < M) {
+      const float2* p = reinterpret_cast<const float2*>(part + (size_t)row * slots);
+      float2 v[4];
+#pragma unroll
+      for (int s = 0; s < 4; ++s) v[s] = 2 * s < slots ? __ldg(p + s) : make_float2(0.f, 0.f);   // independent loads, fixed order
+#pragma unroll
+      for (int s = 0; s < 4; ++s) q += v[s].x, q += v[s].y;
+      for (int s = 8; s < slots; ++s) q += __ldg(part + (size_t)row * slots + s);
+    }
     return RowState{rsqrtf(q * inv_rows + 1e-5f)};
   }
-  __device__ __forceinline__ void transform(int, int col0, float* v, int, int, RowState& st) const {
+  __device__ __forceinline__ void transform_pack(int, int col0, const float* v, uint32_t* out, int, int, RowState& st) const {
     const float rs = st.rstd;
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
       const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + col0 + i));
       const float4 b = __ldg(reinterpret_cast<const float4*>(bgamma + col0 + i));
       const float4 t = __ldg(reinterpret_cast<const float4*>(beta + col0 + i));
-      v[i] = gelu_bf16(fmaf(rs, fmaf(v[i], g.x, b.x), t.x));
-      v[i + 1] = gelu_bf16(fmaf(rs, fmaf(v[i + 1], g.y, b.y), t.y));
-      v[i + 2] = gelu_bf16(fmaf(rs, fmaf(v[i + 2], g.z, b.z), t.z));
-      v[i + 3] = gelu_bf16(fmaf(rs, fmaf(v[i + 3], g.w, b.w), t.w));
+      const __half2 h0 = gelu_h2(__floats2half2_rn(fmaf(rs, fmaf(v[i], g.x, b.x), t.x), fmaf(rs, fmaf(v[i + 1], g.y, b.y), t.y)));
+      const __half2 h1 = gelu_h2(__floats2half2_rn(fmaf(rs, fmaf(v[i + 2], g.z, b.z), t.z), fmaf(rs, fmaf(v[i + 3], g.w, b.w), t.w)));
+      out[i / 2] = *reinterpret_cast<const uint32_t*>(&h0);
+      out[i / 2 + 1] = *reinterpret_cast<const uint32_t*>(&h1);
     }
   }
   __device__ __forceinline__ void row_end(int, int, RowState&, int) const {}
 };
+
+// fp32 (rows, cols) -> fp16, same shape (second linear of the node MLP: its A operand is the fp16 intermediate above)
+__global__ void gin_f32_to_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, size_t total) {
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x)
+    dst[idx] = __float2half_rn(src[idx]);
+}
 
 // Per-graph pooling over the contiguous node range (graph_encoder/model.py:148,152): max -> bf16 operand of the
 // virtual-node MLP, sum -> fp32 (+bf16) read-out.  grid (B, ceil(H/256)).
@@ -415,6 +434,15 @@ __global__ void __launch_bounds__(256) gin_pool_kernel(const float* __restrict__
   if (beg == end) acc = 0.f;
   if (out_f32) out_f32[(size_t)g * H + c] = acc;
   if (out_bf16) out_bf16[(size_t)g * H + c] = __float2bfloat16(acc);
+}
+
+// Per-graph maxima accumulated by the fused layer tail (order-preserving uint encoding, 0 = no node seen) -> bf16 operand of
+// the virtual-node MLP.
+__global__ void gin_pool_decode_kernel(const uint32_t* __restrict__ enc, __nv_bfloat16* __restrict__ out, size_t total) {
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t e = enc[idx];
+    out[idx] = __float2bfloat16(e == 0u ? 0.f : __uint_as_float(float_order_dec(e)));
+  }
 }
 
 // SiLU(c) -> bf16 (adapter operand, graph_predictor/model.py:247-252); c == null broadcasts text_dropping (:315-316).
@@ -787,6 +815,8 @@ struct llb_gin {
   float* head_out = nullptr;
   float* logits_ws = nullptr;
   int32_t* topk_redo = nullptr;   // per row of a logits chunk: redo with the selection-pass kernel
+  uint32_t* pool_enc = nullptr;   // (B,H) per-graph maxima from the fused layer tail (encoded)
+  void* tail_sync = nullptr;      // statistics-exchange workspace of the fused layer tail
   int chunk_rows = 0;
   template <class T>
   const T* w(size_t off) const { return reinterpret_cast<const T*>(blob + off); }
@@ -816,6 +846,8 @@ static int gin_carve(llb_gin* g, void* ws, size_t ws_bytes, int n, int e, int B,
     g->ctext = a.take<__nv_bfloat16>((size_t)B * G.tdim);
   }
   g->pooled = a.take<float>((size_t)B * H), g->pooled_b = a.take<__nv_bfloat16>((size_t)B * H);
+  g->pool_enc = a.take<uint32_t>((size_t)B * H);
+  g->tail_sync = a.take<uint8_t>(gemm_ln_pair_workspace_bytes());
   g->hz = a.take<__nv_bfloat16>((size_t)B * G.HH);
   if (!G.predictor) g->head_out = a.take<float>((size_t)B * H);
   g->chunk_rows = B < TOPK_CHUNK ? B : TOPK_CHUNK;
@@ -854,7 +886,7 @@ static int gin_scan(llb_gin* g, cudaStream_t s) {
 
 static int gin_mlp4(llb_gin* g, const __nv_bfloat16* in, int rows, size_t w0, size_t b0, size_t lnw, size_t lnb, size_t w4, size_t b4,
                     int hidden, int out_f, __nv_bfloat16* zbuf, float* out, int out_ld, cudaStream_t s, int slot0 = LLB_PROF_GIN_MISC,
-                    int slot4 = LLB_PROF_GIN_MISC, int gram_layer = -1) {
+                    int slot4 = LLB_PROF_GIN_MISC, int gram_layer = -1, bool first_half_only = false) {
   // Linear -> LayerNorm(hidden) -> GELU -> Linear  (the 4H MLP of GINConv / virtual node / heads)
   const int H = g->G.H;
   if (gram_layer >= 0) {
@@ -869,7 +901,10 @@ static int gin_mlp4(llb_gin* g, const __nv_bfloat16* in, int rows, size_t w0, si
                  g->chol_c0[gram_layer], 1.0f / (float)hidden};
     LLB_TRY((launch_gemm<256>(in, H, g->w<void>(w0), H, rows, hidden, H, el, s, &g->ctr)));
     g->ctr.slot = slot4;
-    return gemm_bias_act(zbuf, hidden, g->w<void>(w4), hidden, g->w<float>(b4), out, out_ld, rows, out_f, hidden, LLB_ACT_NONE, true, s, &g->ctr);
+    if (first_half_only) return LLB_OK;   // the caller fuses the second linear with the layer tail
+    GemmGroups f16;
+    f16.ab_f16 = true;   // fp16 intermediate x fp16 weight
+    return gemm_bias_act(zbuf, hidden, g->w<void>(w4), hidden, g->w<float>(b4), out, out_ld, rows, out_f, hidden, LLB_ACT_NONE, true, s, &g->ctr, f16);
   }
   g->ctr.slot = slot0;
   LLB_TRY(gemm_bias_act(in, H, g->w<void>(w0), H, g->w<float>(b0), zbuf, hidden, rows, hidden, H, LLB_ACT_NONE, false, s, &g->ctr));
@@ -913,11 +948,20 @@ static int gin_trunk(llb_gin* g, const float* c, cudaStream_t s) {
     }
     LLB_CUDA_OK(cudaGetLastError());
     g->launches++;
+    // LLB_GIN_FUSED_TAIL=0: second linear + row kernel instead of the fused GEMM + layer-tail kernel (launch_gin_tail)
+    static const bool tail_env_off = getenv("LLB_GIN_FUSED_TAIL") && getenv("LLB_GIN_FUSED_TAIL")[0] == '0';
+    const bool fused_tail = !tail_env_off && gin_tail_supported(H, 4 * H);
     if (!last) {
-      // virtual node of the next layer from the max-pool of this layer's INPUT (model.py:148 / :343)
+      // virtual node of the next layer from the max-pool of this layer's INPUT (model.py:148 / :343): the fused tail of the
+      // previous layer has already accumulated it while it wrote that input; layer 0 (and the unfused path) pool explicitly
       {
         ProfScope prof(LLB_PROF_GIN_POOL, s);
-        gin_pool_kernel<<<dim3(B, ceil_div(H, 256)), 256, 0, s>>>(g->h, g->graph_ptr, H, 1, nullptr, g->pool_b);
+        if (fused_tail && l > 0) {
+          const size_t total = (size_t)B * H;
+          gin_pool_decode_kernel<<<(unsigned)(ceil_div((int)(total / 4), 256) < 2048 ? ceil_div((int)(total / 4), 256) : 2048), 256, 0, s>>>(g->pool_enc, g->pool_b, total);
+        } else {
+          gin_pool_kernel<<<dim3(B, ceil_div(H, 256)), 256, 0, s>>>(g->h, g->graph_ptr, H, 1, nullptr, g->pool_b);
+        }
       }
       LLB_CUDA_OK(cudaGetLastError());
       g->launches++;
@@ -930,27 +974,44 @@ static int gin_trunk(llb_gin* g, const float* c, cudaStream_t s) {
       LLB_TRY(launch_row_ln(a, s));
       g->launches++;
     }
-    // LayerNorm + GELU of the node MLP in the first linear's epilogue, from analytic row statistics (see EpiRowSq).
-    // LLB_GIN_ANALYTIC_LN=0 selects the unfused GEMM -> row kernel -> GEMM path (same centred weights: LayerNorm is shift-invariant).
-    static const bool analytic_ln = !(getenv("LLB_GIN_ANALYTIC_LN") && getenv("LLB_GIN_ANALYTIC_LN")[0] == '0');
+    // LayerNorm + GELU of the node MLP in the first linear's epilogue, from analytic row statistics (see EpiRowSq); the
+    // intermediate is fp16 and the second linear multiplies it by the fp16 copy of its weight
     LLB_TRY(gin_mlp4(g, g->agg, n, G.mlp0_w[l], G.mlp0_b[l], G.mlp_ln_w[l], G.mlp_ln_b[l], G.mlp4_w[l], G.mlp4_b[l], 4 * H, H, g->z,
-                     g->u, H, s, LLB_PROF_GIN_GEMM_MLP0, LLB_PROF_GIN_GEMM_MLP4, analytic_ln ? l : -1));
-    RowLnArgs a;
-    a.in = g->u, a.in_ld = H, a.rows = n, a.width = H;
-    a.row_group = g->batch32;
-    if (G.predictor) {
-      const float* mod = g->mod + (size_t)l * B * 3 * H;
-      a.shift = mod, a.scale = mod + H, a.gate = mod + 2 * H, a.mod_ld = 3 * H;
+                     g->u, H, s, LLB_PROF_GIN_GEMM_MLP0, LLB_PROF_GIN_GEMM_MLP4, l, fused_tail));
+    const float* mod = G.predictor ? g->mod + (size_t)l * B * 3 * H : nullptr;
+    if (fused_tail) {
+      // second linear + LayerNorm + affine / text-adaLN + GELU + gate + residual + next virtual node in ONE kernel; it also
+      // accumulates the per-graph maxima of the rows it writes whenever the next layer has a virtual-node update to feed
+      const bool want_pool = l + 1 < L - 1;
+      if (want_pool) LLB_CUDA_OK(cudaMemsetAsync(g->pool_enc, 0, (size_t)B * H * 4, s));
+      GinTailArgs t{};
+      t.bias = g->w<float>(G.mlp4_b[l]), t.row_group = g->batch32;
+      if (G.predictor) t.shift = mod, t.scale = mod + H, t.gate = mod + 2 * H, t.mod_ld = 3 * H;
+      else t.gamma = g->w<float>(G.norm_w[l]), t.beta = g->w<float>(G.norm_b[l]);
+      if (!last) t.addvec = g->vn_next, t.addvec_ld = H;
+      t.act = last ? LLB_ACT_NONE : LLB_ACT_GELU;
+      t.x = g->h, t.ldx = H, t.xb = g->hb, t.ldxb = H;
+      t.pool_max = want_pool ? g->pool_enc : nullptr, t.pool_ld = H;
+      t.a_f16 = 1;
+      g->ctr.slot = LLB_PROF_GIN_GEMM_MLP4;
+      LLB_TRY(launch_gin_tail(g->z, 4 * H, g->w<void>(G.mlp4_w[l]), 4 * H, n, H, 4 * H, t, g->tail_sync, gemm_ln_pair_workspace_bytes(), s, &g->ctr));
     } else {
-      a.gamma = g->w<float>(G.norm_w[l]), a.beta = g->w<float>(G.norm_b[l]);
+      RowLnArgs a;
+      a.in = g->u, a.in_ld = H, a.rows = n, a.width = H;
+      a.row_group = g->batch32;
+      if (G.predictor) {
+        a.shift = mod, a.scale = mod + H, a.gate = mod + 2 * H, a.mod_ld = 3 * H;
+      } else {
+        a.gamma = g->w<float>(G.norm_w[l]), a.beta = g->w<float>(G.norm_b[l]);
+      }
+      a.act = last ? LLB_ACT_NONE : LLB_ACT_GELU;
+      a.resid = g->h, a.resid_ld = H;
+      if (!last) a.addvec = g->vn_next, a.addvec_ld = H;
+      a.out_f32 = g->h, a.out_f32_ld = H, a.out_bf16 = g->hb, a.out_bf16_ld = H;
+      a.prof_slot = LLB_PROF_GIN_ROWLN;
+      LLB_TRY(launch_row_ln(a, s));
+      g->launches++;
     }
-    a.act = last ? LLB_ACT_NONE : LLB_ACT_GELU;
-    a.resid = g->h, a.resid_ld = H;
-    if (!last) a.addvec = g->vn_next, a.addvec_ld = H;
-    a.out_f32 = g->h, a.out_f32_ld = H, a.out_bf16 = g->hb, a.out_bf16_ld = H;
-    a.prof_slot = LLB_PROF_GIN_ROWLN;
-    LLB_TRY(launch_row_ln(a, s));
-    g->launches++;
     if (!last) std::swap(g->vn_cur, g->vn_next);
   }
   {
@@ -989,7 +1050,8 @@ int llb_gin_pack_weights(const llb_gin_config* cfg, const llb_gin_weights* w, vo
   LLB_CUDA_OK(cp(G.atom_emb, w->atom_emb, (size_t)ATOM_VOCAB * H));
   LLB_CUDA_OK(cp(G.vn_emb, w->vn_emb, H));
   for (int l = 0; l < G.L; ++l) {
-    LLB_TRY(launch_f32_to_bf16(w->mlp4_w[l], 4 * H, bf(G.mlp4_w[l]), 4 * H, H, 4 * H, 4 * H, s));
+    gin_f32_to_f16_kernel<<<1024, 256, 0, s>>>(w->mlp4_w[l], reinterpret_cast<__half*>(base + G.mlp4_w[l]), (size_t)4 * H * H);   // fp16: see EpiLnGelu
+    LLB_CUDA_OK(cudaGetLastError());
     LLB_CUDA_OK(cp(G.eps[l], w->eps[l], 1));
     LLB_CUDA_OK(cp(G.mlp_ln_w[l], w->mlp_ln_w[l], 4 * H));
     LLB_CUDA_OK(cp(G.mlp_ln_b[l], w->mlp_ln_b[l], 4 * H));
