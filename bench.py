@@ -257,9 +257,12 @@ def main():
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and not os.environ.get("LLB_KEEP_NCCL_DEBUG"):
-            os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the single JSON line
+        # NCCL_DEBUG (e.g. INFO, which the driver uses to count ranks) is left as the caller set it; NCCL prints to stdout by
+        # default, which must stay ONE JSON line, so its log goes to stderr unless the caller chose a file
+        if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
+            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
         dist.init_process_group("nccl", device_id=device)
+        log(f"[bench] rank {rank}/{world} on cuda:{local_rank}: NCCL process group initialised (nranks={world})")
 
     def barrier():
         if world > 1:
@@ -293,10 +296,16 @@ def main():
     n_nodes = torch.full((B,), N, dtype=torch.int64)
     props_d = props_h.to(device)
     props_d = torch.where(props_d == -200.0, torch.full_like(props_d, float("nan")), props_d).contiguous()
+    from llamole_b200 import sharding
+
     eng.begin(n_nodes.to(torch.int32), props_d, txt_h.to(device).contiguous(), mol_index_base=rank * B)
     eng.init_state(7, None, None)
     for i in range(args.warmup):
         eng.step(T - i, 7)
+    n_dev = n_nodes.to(device)
+    if world > 1:   # untimed: NCCL communicator / buffers of the one exchange of the path
+        Xs, Es = eng.get_state()
+        sharding.all_gather_rows(sharding.pack_graphs(Xs.long(), Es.long(), n_dev))
     barrier()
     launches0 = eng.launch_count()
     _cabi.profile_enable(True)
@@ -306,15 +315,19 @@ def main():
         ev0.record()
         for i in range(args.steps):
             eng.step(T - ((args.warmup + i) % T), 7)
-        if world > 1:   # the path's one exchange: gather the sampled graphs (done once per sampling run)
+        evc = torch.cuda.Event(enable_timing=True)
+        evc.record()
+        if world > 1:
+            # the path's one exchange (once per sampling run), through the product API: the sampled graphs travel as the
+            # packed byte rows of sharding.pack_graphs (1327 B per molecule) in ONE NCCL all-gather and are unpacked on arrival
             Xs, Es = eng.get_state()
-            gx = [torch.empty_like(Xs) for _ in range(world)]
-            ge = [torch.empty_like(Es) for _ in range(world)]
-            dist.all_gather(gx, Xs)
-            dist.all_gather(ge, Es)
+            wire = sharding.all_gather_rows(sharding.pack_graphs(Xs.long(), Es.long(), n_dev))
+            Xg, Eg, ng = sharding.unpack_graphs(wire, N)
+            assert Xg.shape[0] == world * B
         ev1.record()
         barrier()
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    comm_ms = max_over_ranks(evc.elapsed_time(ev1)) if world > 1 else 0.0
     prof = _cabi.profile_read()
     _cabi.profile_enable(False)
     dit_launches = eng.launch_count() - launches0
@@ -341,9 +354,20 @@ def main():
     k_e2e = min(args.steps, 10)
     outX = torch.empty((B, N), dtype=torch.int64).pin_memory()
     outE = torch.empty((B, N, N), dtype=torch.int64).pin_memory()
+    if world > 1:
+        # every rank holds the conditions of the WHOLE job (world x B molecules, the same seeds on every rank) and calls the
+        # product entry point: it samples its own shard and receives everybody's graphs through the packed all-gather
+        parts = [synth.dit_conditions(B, seed=2024 + r) for r in range(world)]
+        props_all = torch.cat([p for p, _ in parts]).pin_memory()
+        txt_all = torch.cat([t for _, t in parts]).pin_memory()
+        n_all = torch.full((world * B,), N, dtype=torch.int64)
     barrier()
     t0 = time.perf_counter()
-    X, E, _ = m.generate_graphs(props_h, txt_h, -200, n_nodes=n_nodes, seed=7, steps=k_e2e, mol_index_base=rank * B)
+    if world > 1:
+        X, E, _ = sharding.sample_graphs_sharded(m.generate_graphs, props_all, txt_all, n_all, seed=7, steps=k_e2e)
+        X, E = X[rank * B:(rank + 1) * B], E[rank * B:(rank + 1) * B]
+    else:
+        X, E, _ = m.generate_graphs(props_h, txt_h, -200, n_nodes=n_nodes, seed=7, steps=k_e2e, mol_index_base=rank * B)
     outX.copy_(X, non_blocking=True)
     outE.copy_(E, non_blocking=True)
     barrier()
@@ -352,7 +376,10 @@ def main():
     h2d = (props_h.numel() + txt_h.numel()) * 4 + B * 4
     d2h = (outX.numel() + outE.numel()) * 8
     e2e = {"value": e2e_val, "unit": "molecules/s", "h2d_bytes_per_step": h2d / k_e2e, "d2h_bytes_per_step": d2h / k_e2e,
-           "note": f"GraphDiT.generate_graphs(host tensors, steps={k_e2e}) + D2H of the integer graphs; one call's copies amortised over its {k_e2e} reverse steps"}
+           "note": (f"GraphDiT.generate_graphs(host tensors, steps={k_e2e}) + D2H of the integer graphs; one call's copies amortised over its {k_e2e} reverse steps"
+                    if world == 1 else
+                    f"sharding.sample_graphs_sharded(GraphDiT.generate_graphs, host tensors of all {world * B} molecules, steps={k_e2e}): own shard sampled, "
+                    "all graphs gathered as packed byte rows over NCCL, + D2H of this rank's graphs")}
     del X, E
     # ------------------------------------------------------------------ the same batch size with ragged molecules
     # SURVEY.md section 8d asks for the padded-N figure (the headline above) AND the figure over actual n_i: node counts
@@ -377,6 +404,33 @@ def main():
                   "mean_atoms": float(n_rag.double().mean()), "tokens_per_pass": int(n_rag.sum()),
                   "achieved_tflops": rag_flops / (rag_ms / 1e3) / 1e12, "frac_of_sustained": rag_flops / (rag_ms / 1e3) / (pk["tf_sustained"] * 1e12),
                   "note": "node counts ~ the (synthetic) checkpoint histogram, uniform on 5..N; varlen packing: only valid atoms are computed"}
+    # ------------------------------------------------------------------ latency regime (BASELINE.json configs[0]: B = 16; the
+    # reference's own call pattern: B = 6 = per_device_eval_batch_size of config/generate/*.yaml, modeling_llamole.py:653)
+    latency = None
+    if not args.small:
+        weight_bytes = sum(p.numel() for n_, p in m.denoiser.named_parameters() if p.dim() == 2) * 2    # bf16 GEMM operands streamed once per step
+        floor_ms = weight_bytes / (pk["hbm"] * 1e9) * 1e3
+        latency = {"weight_bytes": weight_bytes, "weight_streaming_floor_ms": floor_ms, "batches": {}}
+        for Bl in (6, 16):
+            pl, tl = synth.dit_conditions(Bl, seed=900 + Bl)
+            pl = torch.where(pl == -200.0, torch.full_like(pl, float("nan")), pl).to(device).contiguous()
+            n_l = m.sample_n_nodes(Bl, generator=torch.Generator().manual_seed(5 + Bl)).clamp_(min=10)
+            eng.begin(n_l.to(torch.int32), pl, tl.to(device).contiguous(), mol_index_base=0)
+            eng.init_state(7, None, None)
+            for i in range(5):
+                eng.step(T - i, 7)
+            torch.cuda.synchronize()
+            k_lat = 50
+            ev0.record()
+            for i in range(k_lat):
+                eng.step(T - 5 - i, 7)
+            ev1.record()
+            torch.cuda.synchronize()
+            ms_l = ev0.elapsed_time(ev1) / k_lat
+            latency["batches"][str(Bl)] = {"ms_per_step": ms_l, "molecules_per_s": Bl / (T * ms_l / 1e3), "token_rows": 2 * int(n_l.sum()),
+                                           "floor_frac": floor_ms / ms_l, "steps": k_lat}
+        latency["note"] = ("one reverse step (cond + uncond pass batched, posterior, sampling) at the reference's per-prompt batch sizes; "
+                           "floor = streaming the bf16 weights once per step at the measured HBM peak")
     # ------------------------------------------------------------------ GIN encoder
     gin = bench_gin(args, device, rank, world, barrier, max_over_ranks, pk)
     pred = None
@@ -391,12 +445,18 @@ def main():
         cpu = {"value": 16 / (T * sec), "unit": "molecules/s", "cores": cores, "kind": "port",
                "sample": f"16 of {B} molecules, 3 reverse steps after 1 warm-up ({sec:.2f} s/step), scaled to T={T}; oracle/llamole_oracle.py in fp32"}
         gin["cpu_baseline"] = gin_cpu_baseline(gin)
+        if pred is not None:
+            pred["cpu_baseline"] = predictor_cpu_baseline(args)
         log(f"cpu baseline took {time.time() - t0:.1f}s")
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": "molecules/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic", "config": workload_config(args), "clocks": clocks.summary(), "e2e": e2e,
+            "comm": {"backend": "nccl" if world > 1 else None, "nranks": world, "comm_ms": comm_ms, "comm_ms_per_step": comm_ms / args.steps,
+                     "what": "one all-gather of the packed sampled graphs (sharding.pack_graphs, 1327 B/molecule) + unpack, once per sampling run; "
+                             "included in ms_per_step" if world > 1 else "single GPU: no exchange"},
+            "latency": latency,
             "gpu_launches": int(dit_launches + gin.pop("_launches") + (pred.pop("_launches") if pred else 0)), "roofline": roofline,
             "cpu_baseline": cpu, "kernel_breakdown": breakdown, "ragged": ragged, "gin": gin, "predictor": pred,
         }
@@ -413,6 +473,35 @@ def gin_cpu_baseline(gin):
     sec = cpu_gin_seconds(enc, proj, graphs)
     return {"value": 512 / sec, "unit": "graphs/s", "cores": torch.get_num_threads(), "kind": "port",
             "sample": "first 512 of the 4096 graphs, one GraphCLIP forward, oracle/llamole_oracle.py in fp32"}
+
+
+def predictor_cpu_baseline(args):
+    """the predictor on a 512-graph subset, oracle port in fp32 on the host cores; the head is evaluated on
+    a 16 384-template slice of the weight and its time scaled to out_dim (a Linear's cost is proportional to its rows)."""
+    from llamole_b200 import synth
+    from oracle import llamole_oracle as O
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    H, L, Ds = GIN["hidden"], GIN["layers"], 16384
+    sd = synth.gin_predictor_state_dict(L, H, Ds, seed=13)
+    x, ei, ea, b = synth.molecular_graphs(512, seed=100)
+    c = synth.text_conditions(512, seed=7)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        logits = O.gin_predictor_forward(sd, L, x, ei, ea, b, c)
+        t_all = time.perf_counter() - t0
+        hid = torch.randn(512, 4 * H)
+        t0 = time.perf_counter()
+        torch.nn.functional.linear(hid, sd["decoder.4.weight"], sd["decoder.4.bias"])
+        t_head = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        O.predictor_topk(logits, 50)
+        t_topk = time.perf_counter() - t0
+    scale = args.pred_out_dim / Ds
+    sec = (t_all - t_head) + (t_head + t_topk) * scale
+    return {"value": 512 / sec, "unit": "graphs/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"512 of {args.pred_graphs} graphs, one GNNRetrosynthsizer forward + softmax/top-50, oracle/llamole_oracle.py in fp32; head and top-k "
+                      f"timed on {Ds} of the {args.pred_out_dim} templates and scaled by {scale:.2f} (trunk {t_all - t_head:.2f} s, head {t_head:.2f} s, top-k {t_topk:.2f} s)"}
 
 
 def bench_predictor(args, device, rank, world, barrier, max_over_ranks, pk):
@@ -447,19 +536,43 @@ def bench_predictor(args, device, rank, world, barrier, max_over_ranks, pk):
     for _ in range(iters):
         eng.bind(xd, eid, ead, bd, num_graphs=G, want_logits=True, validate=False)
         probs, idx = eng.predictor_topk(c, k)
-    if world > 1:   # the one exchange of the path: gather the candidates' top-k
-        import torch.distributed as dist
+    if world > 1:   # the one exchange of the path: gather the candidates' top-k (product helper, one padded all-gather)
+        from llamole_b200 import sharding
 
-        gp = [torch.empty_like(probs) for _ in range(world)]
-        gi = [torch.empty_like(idx) for _ in range(world)]
-        dist.all_gather(gp, probs)
-        dist.all_gather(gi, idx)
+        sharding.all_gather_rows(torch.cat([probs, idx.to(torch.float32)], dim=1))
     ev1.record()
     barrier()
     ms = max_over_ranks(ev0.elapsed_time(ev1)) / iters
     prof = _cabi.profile_read()
     _cabi.profile_enable(False)
     launches = eng.launch_count() - l0
+    # strong scaling of BASELINE.json configs[3]: 65 536 reactant graphs in total, 65 536 / N per GPU (the local batch repeated with
+    # node offsets; same graph statistics), one bind + top-50 pass + gather
+    strong = None
+    total_graphs = 65536
+    if total_graphs % (world * G) == 0 or total_graphs // world >= G:
+        reps_s = max(1, total_graphs // world // G)
+        Gs = reps_s * G
+        xs = xd.repeat(reps_s)
+        eas = ead.repeat(reps_s)
+        eis = torch.cat([eid + r * n for r in range(reps_s)], dim=1)
+        bs = torch.cat([bd + r * G for r in range(reps_s)])
+        cs = c.repeat(reps_s, 1)
+        for _ in range(2):
+            eng.bind(xs, eis, eas, bs, num_graphs=Gs, want_logits=True, validate=False)
+            ps, is_ = eng.predictor_topk(cs, k)
+        barrier()
+        ev0.record()
+        eng.bind(xs, eis, eas, bs, num_graphs=Gs, want_logits=True, validate=False)
+        ps, is_ = eng.predictor_topk(cs, k)
+        if world > 1:
+            sharding.all_gather_rows(torch.cat([ps, is_.to(torch.float32)], dim=1))
+        ev1.record()
+        barrier()
+        ms_s = max_over_ranks(ev0.elapsed_time(ev1))
+        strong = {"total_graphs": world * Gs, "graphs_per_gpu": Gs, "ms": ms_s, "value": world * Gs / (ms_s / 1e3), "unit": "graphs/s", "scaling": "strong",
+                  "note": "fixed total of 65 536 candidate graphs split over the GPUs; compare `ms` across N"}
+        del xs, eas, eis, bs, cs, ps, is_
     # e2e: host graphs + conditions -> top-k on the host
     xp, eip, eap, bp, cp = (t.pin_memory() for t in (x, ei, ea, batch, c.cpu()))
     hp = torch.empty((G, k), dtype=torch.float32).pin_memory()
@@ -487,6 +600,7 @@ def bench_predictor(args, device, rank, world, barrier, max_over_ranks, pk):
                      "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": head_flops / (head_ms / 1e3) / 1e12 / pk["tf_sustained"] if head_ms else None,
                      "traffic": None, "peak_source": pk["source"], "flops_per_batch": head_flops, "whole_batch_tflops": (trunk_flops + head_flops) / (ms / 1e3) / 1e12},
         "kernel_breakdown": {k_: {"ms_per_batch": v[0] / iters, "launches": v[1] / iters} for k_, v in prof.items() if k_.startswith("gin_")},
+        "strong_scaling": strong,
         "_launches": launches,
     }
     del m, eng
@@ -547,7 +661,11 @@ def bench_gin(args, device, rank, world, barrier, max_over_ranks, pk):
                      "unit": "GB/s", "frac": agg_bytes / (agg_ms / 1e3) / 1e9 / pk["hbm"], "traffic": ncu_traffic("gin_aggregate"), "launch_ms": agg_ms,
                      "bytes_per_launch": agg_bytes, "peak_source": pk["source"]},
         "mlp_gemms": {"tflops": mlp_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms else None, "frac_of_sustained": mlp_flops / (gemm_ms / 1e3) / 1e12 / pk["tf_sustained"] if gemm_ms else None,
-                      "ms_per_forward": gemm_ms},
+                      "ms_per_forward": gemm_ms,
+                      "note": "algorithmic FLOPs of the node / virtual-node / projection MLPs (SURVEY.md 8d) over the time of the mlp0 and mlp4 slots; the "
+                              "mlp4 slot is the fused GEMM + layer-tail kernel, the statistics GEMM of the analytic LayerNorm (gin_gemm_stats) is extra work"},
+        "whole_forward": {"tflops": mlp_flops / (ms / 1e3) / 1e12, "frac_of_sustained": mlp_flops / (ms / 1e3) / 1e12 / pk["tf_sustained"],
+                          "note": "algorithmic MLP FLOPs over the whole forward (CSR build, aggregation, GEMMs, pooling, head)"},
         "kernel_breakdown": {k: {"ms_per_forward": v[0] / iters, "launches": v[1] / iters} for k, v in prof.items()},
         "_launches": launches,
     }
