@@ -305,7 +305,7 @@ def main():
     n_dev = n_nodes.to(device)
     if world > 1:   # untimed: NCCL communicator / buffers of the one exchange of the path
         Xs, Es = eng.get_state()
-        sharding.all_gather_rows(sharding.pack_graphs(Xs.long(), Es.long(), n_dev))
+        sharding.all_gather_rows(sharding.pack_graphs(Xs, Es, n_dev, check=False), sizes=[B] * world)
     barrier()
     launches0 = eng.launch_count()
     _cabi.profile_enable(True)
@@ -321,7 +321,7 @@ def main():
             # the path's one exchange (once per sampling run), through the product API: the sampled graphs travel as the
             # packed byte rows of sharding.pack_graphs (1327 B per molecule) in ONE NCCL all-gather and are unpacked on arrival
             Xs, Es = eng.get_state()
-            wire = sharding.all_gather_rows(sharding.pack_graphs(Xs.long(), Es.long(), n_dev))
+            wire = sharding.all_gather_rows(sharding.pack_graphs(Xs, Es, n_dev, check=False), sizes=[B] * world)
             Xg, Eg, ng = sharding.unpack_graphs(wire, N)
             assert Xg.shape[0] == world * B
         ev1.record()
@@ -539,13 +539,14 @@ def bench_predictor(args, device, rank, world, barrier, max_over_ranks, pk):
     if world > 1:   # the one exchange of the path: gather the candidates' top-k (product helper, one padded all-gather)
         from llamole_b200 import sharding
 
-        sharding.all_gather_rows(torch.cat([probs, idx.to(torch.float32)], dim=1))
+        sharding.all_gather_rows(torch.cat([probs, idx.to(torch.float32)], dim=1), sizes=[G] * world)
     ev1.record()
     barrier()
     ms = max_over_ranks(ev0.elapsed_time(ev1)) / iters
     prof = _cabi.profile_read()
     _cabi.profile_enable(False)
     launches = eng.launch_count() - l0
+    head_stats = eng.head_stats()
     # strong scaling of BASELINE.json configs[3]: 65 536 reactant graphs in total, 65 536 / N per GPU (the local batch repeated with
     # node offsets; same graph statistics), one bind + top-50 pass + gather
     strong = None
@@ -566,7 +567,7 @@ def bench_predictor(args, device, rank, world, barrier, max_over_ranks, pk):
         eng.bind(xs, eis, eas, bs, num_graphs=Gs, want_logits=True, validate=False)
         ps, is_ = eng.predictor_topk(cs, k)
         if world > 1:
-            sharding.all_gather_rows(torch.cat([ps, is_.to(torch.float32)], dim=1))
+            sharding.all_gather_rows(torch.cat([ps, is_.to(torch.float32)], dim=1), sizes=[Gs] * world)
         ev1.record()
         barrier()
         ms_s = max_over_ranks(ev0.elapsed_time(ev1))
@@ -600,7 +601,7 @@ def bench_predictor(args, device, rank, world, barrier, max_over_ranks, pk):
                      "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": head_flops / (head_ms / 1e3) / 1e12 / pk["tf_sustained"] if head_ms else None,
                      "traffic": None, "peak_source": pk["source"], "flops_per_batch": head_flops, "whole_batch_tflops": (trunk_flops + head_flops) / (ms / 1e3) / 1e12},
         "kernel_breakdown": {k_: {"ms_per_batch": v[0] / iters, "launches": v[1] / iters} for k_, v in prof.items() if k_.startswith("gin_")},
-        "strong_scaling": strong,
+        "strong_scaling": strong, "head": head_stats,
         "_launches": launches,
     }
     del m, eng

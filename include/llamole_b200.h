@@ -285,6 +285,10 @@ int llb_gin_predictor_forward(llb_gin* h, const float* c, float* logits, llb_str
 int llb_gin_predictor_topk(llb_gin* h, const float* c, int k, float* topk_prob, int32_t* topk_idx,
                            llb_stream_t stream);
 int64_t llb_gin_launch_count(const llb_gin* h);
+/* Statistics of the last llb_gin_predictor_topk call on this handle: rows that went through the fused head + softmax + top-k
+ * kernel, and how many of those fell back to the exact materialising path (expected: none). */
+enum { LLB_GIN_STAT_HEAD_FUSED_ROWS = 0, LLB_GIN_STAT_HEAD_FLAGGED_ROWS = 1 };
+int64_t llb_gin_stat(const llb_gin* h, int which);
 /* The softmax + top-k stage on its own (graph_predictor/model.py:177-179: F.softmax(logits, dim=1) then torch.topk):
  * logits (rows, ld) fp32 with W valid columns -> topk_prob / topk_idx (rows, k), value descending, ties to the lowest
  * index.  One streaming pass per row, plus an exact selection-pass redo of the rows flagged in `scratch` (rows int32). */

@@ -97,6 +97,7 @@ SIGNATURES = {
     "llb_gin_predictor_forward": (_I, [_P, _P, _P, _P]),
     "llb_gin_predictor_topk": (_I, [_P, _P, _I, _P, _P, _P]),
     "llb_gin_launch_count": (C.c_int64, [_P]),
+    "llb_gin_stat": (C.c_int64, [_P, _I]),
     "llb_softmax_topk": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "llb_cost_mlp": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P]),
 }

@@ -194,8 +194,10 @@ __device__ __forceinline__ void gemm_epilogue_tile(const Epi& epi, const CUtenso
 template <int BN, bool TMA_STORE, class Epi>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmC, int M, int N, int K, Epi epi, int group_n, int group_k, int group_w, int ab_f16) {
+                    const __grid_constant__ CUtensorMap tmC, int M, int N, int K, Epi epi, int group_n, int group_k, int group_w, int opts) {
   using Cfg = GemmCfg<BN>;
+  const int ab_f16 = opts & 1;
+  const bool m_fast = (opts & 2) != 0;   // walk the tiles m-fastest: a narrow A stays in L2 while a wide W is streamed once
   constexpr int STAGES = Cfg::STAGES;
   constexpr int ELEM = Epi::OUT_F32 ? 4 : 2;
   constexpr int ROW_BYTES = Epi::CHUNK * ELEM;            // 64 or 128
@@ -244,8 +246,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / num_n) * GEMM_BM;
-      const int n0 = (tile % num_n) * BN;
+      const int m0 = (m_fast ? tile % num_m : tile / num_n) * GEMM_BM;
+      const int n0 = (m_fast ? tile / num_m : tile % num_n) * BN;
       // grouped along N: group g reads A columns [g group_k, +K); split-K flavour (group_w): it also reads the SAME W rows
       // at columns [g group_k, +K), i.e. the groups are the K-slices of one linear and C holds their partial products
       const int grp_i = group_n > 0 ? n0 / group_n : 0;
@@ -308,8 +310,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / num_n) * GEMM_BM;
-      const int n0 = (tile % num_n) * BN;
+      const int m0 = (m_fast ? tile % num_m : tile / num_n) * GEMM_BM;
+      const int n0 = (m_fast ? tile / num_m : tile % num_n) * BN;
       const auto rst = gemm_epilogue_row_begin(epi, m0, M);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -394,8 +396,10 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
 template <bool TMA_STORE, class Epi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const __grid_constant__ CUtensorMap tmC, int M, int N, int K, Epi epi, int group_n, int group_k, int group_w, int ab_f16) {
+                         const __grid_constant__ CUtensorMap tmC, int M, int N, int K, Epi epi, int group_n, int group_k, int group_w, int opts) {
   using Cfg = Gemm2Cfg;
+  const int ab_f16 = opts & 1;
+  const bool m_fast = (opts & 2) != 0;   // walk the tiles m-fastest: a narrow A stays in L2 while a wide W is streamed once
   constexpr int STAGES = Cfg::STAGES;
   constexpr int BN = Cfg::BN;
   extern __shared__ uint8_t smem_raw[];
@@ -451,8 +455,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     uint32_t phase = 0;
     int tcount = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++tcount) {
-      const int m0 = (tile / num_n) * (2 * GEMM_BM) + rank * GEMM_BM;
-      const int n0 = (tile % num_n) * BN + rank * (BN / 2);
+      const int m0 = (m_fast ? tile % num_m : tile / num_n) * (2 * GEMM_BM) + rank * GEMM_BM;
+      const int n0 = (m_fast ? tile / num_m : tile % num_n) * BN + rank * (BN / 2);
       const int grp_i = group_n > 0 ? n0 / group_n : 0;   // grouped along N (group_n is a multiple of BN), see the single-CTA kernel
       const int ka0 = grp_i * group_k;
       const int kw0 = group_w ? ka0 : 0, wn0 = group_w ? n0 - grp_i * group_n : n0;
@@ -539,8 +543,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     uint32_t acc_phase = 0;
     int tcount = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++tcount) {
-      const int m0 = (tile / num_n) * (2 * GEMM_BM) + rank * GEMM_BM;
-      const int n0 = (tile % num_n) * BN;
+      const int m0 = (m_fast ? tile % num_m : tile / num_n) * (2 * GEMM_BM) + rank * GEMM_BM;
+      const int n0 = (m_fast ? tile / num_m : tile % num_n) * BN;
       if (warp == 0 && lane == 0) LLB_TRACE(tcount, 6, clock64());
       const auto rst = gemm_epilogue_row_begin(epi, m0, M);
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -585,6 +589,7 @@ struct GemmGroups {
   int group_n = 0, group_k = 0;
   bool split_k = false;
   bool ab_f16 = false;   // both operands are IEEE fp16 instead of bf16 (same tile shapes, same descriptors otherwise)
+  bool m_fastest = false;   // tile order: consecutive CTAs share a W tile (narrow A resident in L2, wide W streamed from HBM once)
 };
 
 struct GemmCounters {
@@ -615,6 +620,9 @@ int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, in
   else tmC = tmA;
   const int tiles = ceil_div(M, GEMM_BM) * ceil_div(N, BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
+  // m-fastest automatically when A fits the L2 comfortably and W does not (the predictor head: 50 MB of activations against a
+  // 1.1 GB weight, which the n-fastest walk would stream from HBM once per 256-row block); never for grouped launches
+  const bool m_fast = grp.group_n == 0 && (grp.m_fastest || ((size_t)M * K * 2 <= ((size_t)64 << 20) && (size_t)N * K * 2 >= ((size_t)256 << 20)));
   static bool configured[4] = {false, false, false, false};  // per template instantiation
   // CTA-pair kernel: wide problems whose 256 x 256 pair-tiles fill the machine
   const int pair_tiles = ceil_div(M, 2 * GEMM_BM) * ceil_div(N, 256);
@@ -629,7 +637,7 @@ int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, in
       }
       const int pairs = pair_tiles < num_sms() / 2 ? pair_tiles : num_sms() / 2;
       ProfScope prof(ctr ? ctr->slot : LLB_PROF_GEMM_OTHER, stream);
-      kern<<<2 * pairs, GEMM_THREADS, Gemm2Cfg::SMEM_BYTES, stream>>>(tmA, tmBh, tmC, M, N, K, epi, grp.group_n, grp.group_k, grp.split_k ? 1 : 0, grp.ab_f16 ? 1 : 0);
+      kern<<<2 * pairs, GEMM_THREADS, Gemm2Cfg::SMEM_BYTES, stream>>>(tmA, tmBh, tmC, M, N, K, epi, grp.group_n, grp.group_k, grp.split_k ? 1 : 0, (grp.ab_f16 ? 1 : 0) | (m_fast ? 2 : 0));
       note_kernel(LLB_KERN_GEMM_2CTA);
       return LLB_OK;
     };
@@ -642,7 +650,7 @@ int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, in
         configured[which] = true;
       }
       ProfScope prof(ctr ? ctr->slot : LLB_PROF_GEMM_OTHER, stream);
-      kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, M, N, K, epi, grp.group_n, grp.group_k, grp.split_k ? 1 : 0, grp.ab_f16 ? 1 : 0);
+      kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, M, N, K, epi, grp.group_n, grp.group_k, grp.split_k ? 1 : 0, (grp.ab_f16 ? 1 : 0) | (m_fast ? 2 : 0));
       note_kernel(LLB_KERN_GEMM_1CTA);
       return LLB_OK;
     };

@@ -19,6 +19,11 @@ namespace {
 
 constexpr int ATOM_VOCAB = 118;
 constexpr int BOND_VOCAB = 5;
+constexpr int HEAD_FUSED_MIN_WIDTH = 16384;   // fused head + softmax + top-k from this many templates on ...
+constexpr int HEAD_FUSED_MIN_ROWS = 512;      // ... and this many graphs (below: materialise the few logit rows, no host sync)
+constexpr int HEAD_PILOT_COLS = 4096;         // strided sample of the templates that fixes each row's threshold
+constexpr int HEAD_CAND_CAP = 2048;           // candidates above the threshold kept per row
+constexpr int HEAD_ROW_CHUNK = 8192;          // rows per fused pass: 50 MB of head inputs stay L2-resident while the weight streams once
 
 struct GinLayout {
   int H, L, predictor, out_dim, tdim, HH, HO;
@@ -28,6 +33,8 @@ struct GinLayout {
   std::vector<size_t> mlp_bg;                                      // fp32 (4H): centred bias x LayerNorm gamma
   size_t chol_scratch;                                             // fp64 (H+1, H+1) Gram matrix, pack time only
   size_t head0_w, head4_w;
+  size_t pilot_w, pilot_b;     // (pilot_cols, HH) bf16 / (pilot_cols) fp32: every pilot_stride-th template of the head (fused top-k)
+  int pilot_cols, pilot_stride;
   size_t atom_emb, vn_emb, text_drop;                             // fp32
   std::vector<size_t> eps, mlp0_b, mlp_ln_w, mlp_ln_b, mlp4_b, bond_emb, norm_w, norm_b;
   std::vector<size_t> vn0_b, vn_ln_w, vn_ln_b, vn4_b, adapter_b;
@@ -81,6 +88,10 @@ int make_layout(const llb_gin_config& c, GinLayout& G) {
   }
   G.head0_b = take((size_t)G.HH * 4), G.head_ln_w = take((size_t)G.HH * 4), G.head_ln_b = take((size_t)G.HH * 4);
   G.head4_b = take((size_t)G.HO * 4);
+  // fused head + top-k (wide predictor heads only): a strided sample of the templates gives every row its threshold
+  G.pilot_cols = (G.predictor && G.out_dim >= HEAD_FUSED_MIN_WIDTH) ? HEAD_PILOT_COLS : 0;
+  G.pilot_stride = G.pilot_cols ? G.out_dim / G.pilot_cols : 0;
+  G.pilot_w = take((size_t)G.pilot_cols * G.HH * 2), G.pilot_b = take((size_t)G.pilot_cols * 4);
   G.chol_scratch = take((H + 1) * (H + 1) * 8);
   G.total = align_up(off, 256);
   return LLB_OK;
@@ -760,6 +771,153 @@ static void launch_softmax_topk(const float* logits, int rows, int W, int ld, in
   gin_topk_kernel<<<rows, 1024, 0, s>>>(logits, ld, W, k, topv, topi, flags);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused predictor head: template logits -> softmax -> top-k WITHOUT the (graphs, out_dim) logits matrix
+// (graph_predictor/model.py:174-179; 5.9 GB written and read back per 8192 graphs at out_dim = 180 576 when materialised).
+//   1. pilot GEMM: logits of every pilot_stride-th template (4096 columns, 2.3 % of the head) -> gin_head_pilot_kernel: per row
+//      m0 = the sample maximum (reference of the softmax sum) and tau = the R-th largest of the sample's 32 warp maxima, R chosen
+//      so that ~7 k templates of the full row are expected above tau (the rule of gin_topk_thresh_kernel);
+//   2. head GEMM with EpiHeadTopk: no output matrix; thread = row adds 2^((x - m0) log2 e) over its columns and appends the
+//      rare x > tau to the row's candidate list; per (N tile, column group) partial sums -> deterministic total;
+//   3. gin_head_select_kernel: total, rank of every candidate by counting (value descending, ties to the lower index) -> top-k.
+// Rows with fewer than k candidates, an overflowing list or a non-finite / zero sum are FLAGGED; the host reads the flag count
+// (the one synchronisation of llb_gin_predictor_topk) and sends flagged rows through the exact materialising path.
+// ---------------------------------------------------------------------------------------------
+__global__ void gin_pilot_pack_kernel(const float* __restrict__ W, const float* __restrict__ b, int K, int stride, int cols,
+                                      __nv_bfloat16* __restrict__ Wp, float* __restrict__ bp) {
+  const int j = blockIdx.x;
+  const float* src = W + (size_t)j * stride * K;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) Wp[(size_t)j * K + k] = __float2bfloat16(src[k]);
+  if (threadIdx.x == 0) bp[j] = b[(size_t)j * stride];
+}
+
+// one CTA of 1024 threads per row of the (rows, 4096) pilot logits -> (tau, m0 * log2 e)
+__global__ void __launch_bounds__(1024) gin_head_pilot_kernel(const float* __restrict__ pilot, int R, float2* __restrict__ rowtau) {
+  __shared__ uint32_t wkey[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float4 q = __ldg(reinterpret_cast<const float4*>(pilot + (size_t)blockIdx.x * HEAD_PILOT_COLS) + tid);
+  const uint32_t key = tk_enc(fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w)));
+  const uint32_t wmax = __reduce_max_sync(0xffffffffu, key);
+  if (lane == 0) wkey[warp] = wmax;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t cur = wkey[lane];
+    const float m0 = tk_dec(__reduce_max_sync(0xffffffffu, cur));
+    uint32_t t = 0;
+    for (int r = 0; r < R; ++r) {   // R-th largest (with multiplicity) of the 32 warp maxima
+      t = __reduce_max_sync(0xffffffffu, cur);
+      const uint32_t holders = __ballot_sync(0xffffffffu, cur == t);
+      if (lane == __ffs(holders) - 1) cur = 0u;
+    }
+    if (lane == 0) rowtau[blockIdx.x] = make_float2(tk_dec(t), m0 * 1.4426950408889634f);
+  }
+}
+
+struct EpiHeadTopk {
+  static constexpr int CHUNK = 32;
+  static constexpr bool OUT_F32 = true;
+  static constexpr bool NO_STORE = true;
+  void* C;     // unused
+  int ldc;     // unused
+  const float* bias;        // (N)
+  const float2* rowtau;     // (M) threshold, m0 * log2 e
+  float* part;              // (M, slots) partial softmax sums
+  int slots;
+  float2* cand;             // (M, HEAD_CAND_CAP) (value, column bits)
+  int32_t* cnt;             // (M) candidates seen (may exceed the capacity)
+  struct RowState {
+    float tau, m0c, s;
+  };
+  __device__ __forceinline__ RowState row_begin(int row, int M) const {
+    const float2 t = row < M ? __ldg(rowtau + row) : make_float2(INFINITY, 0.f);
+    return RowState{t.x, t.y, 0.f};
+  }
+  __device__ __forceinline__ void transform(int row, int col0, float* v, int M, int N, RowState& st) const {
+    constexpr float LOG2E = 1.4426950408889634f;
+    float s0 = 0.f, s1 = 0.f;
+    const bool full = col0 + 32 <= N;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      float4 b;
+      if (full) b = __ldg(reinterpret_cast<const float4*>(bias + col0 + i));
+      else b = make_float4(col0 + i < N ? __ldg(bias + col0 + i) : 0.f, col0 + i + 1 < N ? __ldg(bias + col0 + i + 1) : 0.f,
+                           col0 + i + 2 < N ? __ldg(bias + col0 + i + 2) : 0.f, col0 + i + 3 < N ? __ldg(bias + col0 + i + 3) : 0.f);
+      const float x[4] = {v[i] + b.x, v[i + 1] + b.y, v[i + 2] + b.z, v[i + 3] + b.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const bool in = full || col0 + i + e < N;
+        const float ex = in ? ex2_approx(fmaf(x[e], LOG2E, -st.m0c)) : 0.f;
+        if (e & 1) s1 += ex; else s0 += ex;
+        if (in && x[e] > st.tau && row < M) {   // rare (~350 of 180 576 columns per row)
+          const int p = atomicAdd(cnt + row, 1);
+          if (p < HEAD_CAND_CAP) cand[(size_t)row * HEAD_CAND_CAP + p] = make_float2(x[e], __int_as_float(col0 + i + e));
+        }
+      }
+    }
+    st.s += s0 + s1;
+  }
+  __device__ __forceinline__ void row_end(int row, int slot, RowState& st, int M) const {
+    if (row < M) part[(size_t)row * slots + slot] = st.s;
+  }
+};
+
+// one CTA per row: softmax denominator from the partial sums, top-k of the candidate list by rank counting
+__global__ void __launch_bounds__(256) gin_head_select_kernel(const float* __restrict__ part, int slots, const float2* __restrict__ rowtau,
+                                                              const float2* __restrict__ cand, const int32_t* __restrict__ cnt, int k,
+                                                              float* __restrict__ topv, int32_t* __restrict__ topi, int32_t* __restrict__ flagged,
+                                                              int32_t* __restrict__ n_flagged) {
+  __shared__ float red[8];
+  __shared__ float2 sc[HEAD_CAND_CAP];
+  const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // fixed summation tree: thread t adds slots t, t + 256, ... in order, then warp / block trees
+  float s = 0.f;
+  for (int i = tid; i < slots; i += 256) s += part[(size_t)row * slots + i];
+  s = warp_sum(s);
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  float sum = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) sum += red[w];
+  const int C = cnt[row];
+  if (C < k || C > HEAD_CAND_CAP || !(sum > 0.f) || !(sum < 3.0e38f)) {   // block-uniform
+    if (tid == 0) flagged[atomicAdd(n_flagged, 1)] = row;
+    return;
+  }
+  for (int i = tid; i < C; i += 256) sc[i] = cand[(size_t)row * HEAD_CAND_CAP + i];
+  __syncthreads();
+  const float m0c = rowtau[row].y;
+  const float inv = 1.0f / sum;
+  for (int t = tid; t < C; t += 256) {
+    const float2 me = sc[t];
+    const int mi = __float_as_int(me.y);
+    int rank = 0;
+    for (int j = 0; j < C; ++j) {
+      const float2 o = sc[j];
+      rank += (o.x > me.x || (o.x == me.x && __float_as_int(o.y) < mi)) ? 1 : 0;
+    }
+    if (rank < k) {
+      topv[(size_t)row * k + rank] = ex2_approx(fmaf(me.x, 1.4426950408889634f, -m0c)) * inv;
+      topi[(size_t)row * k + rank] = mi;
+    }
+  }
+}
+
+// flagged rows: gather their head inputs / scatter their exact results
+__global__ void gin_gather_rows_kernel(const __nv_bfloat16* __restrict__ src, const int32_t* __restrict__ rows, int W, __nv_bfloat16* __restrict__ dst) {
+  const int r = rows[blockIdx.x];
+  const uint4* s4 = reinterpret_cast<const uint4*>(src + (size_t)r * W);
+  uint4* d4 = reinterpret_cast<uint4*>(dst + (size_t)blockIdx.x * W);
+  for (int i = threadIdx.x; i < W / 8; i += blockDim.x) d4[i] = s4[i];
+}
+__global__ void gin_scatter_topk_kernel(const float* __restrict__ v, const int32_t* __restrict__ i, const int32_t* __restrict__ rows, int k,
+                                        float* __restrict__ topv, int32_t* __restrict__ topi) {
+  const int r = rows[blockIdx.x];
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    topv[(size_t)r * k + j] = v[(size_t)blockIdx.x * k + j];
+    topi[(size_t)r * k + j] = i[(size_t)blockIdx.x * k + j];
+  }
+}
+
 __global__ void cost_mlp_kernel(const float* __restrict__ w0, const float* __restrict__ b0, const float* __restrict__ w1,
                                 const float* __restrict__ b1, const float* __restrict__ fps, int fp_dim, int latent,
                                 float* __restrict__ out) {
@@ -815,6 +973,18 @@ struct llb_gin {
   float* head_out = nullptr;
   float* logits_ws = nullptr;
   int32_t* topk_redo = nullptr;   // per row of a logits chunk: redo with the selection-pass kernel
+  // fused head + top-k
+  float* pilot_logits = nullptr;   // (fused rows, HEAD_PILOT_COLS)
+  float2* rowtau = nullptr;        // (fused rows)
+  float* head_part = nullptr;      // (fused rows, head_slots)
+  int head_slots = 0, fused_rows = 0;
+  float2* head_cand = nullptr;     // (fused rows, HEAD_CAND_CAP)
+  int32_t *head_cnt = nullptr, *head_flagged = nullptr, *head_nflag = nullptr;
+  __nv_bfloat16* redo_in = nullptr;   // (chunk_rows, HH) gathered head inputs of flagged rows
+  float* redo_v = nullptr;
+  int32_t* redo_i = nullptr;
+  int max_k = 0;
+  int64_t head_flagged_rows = 0, head_fused_rows = 0;   // statistics of the last llb_gin_predictor_topk call
   uint32_t* pool_enc = nullptr;   // (B,H) per-graph maxima from the fused layer tail (encoded)
   void* tail_sync = nullptr;      // statistics-exchange workspace of the fused layer tail
   int chunk_rows = 0;
@@ -850,10 +1020,25 @@ static int gin_carve(llb_gin* g, void* ws, size_t ws_bytes, int n, int e, int B,
   g->tail_sync = a.take<uint8_t>(gemm_ln_pair_workspace_bytes());
   g->hz = a.take<__nv_bfloat16>((size_t)B * G.HH);
   if (!G.predictor) g->head_out = a.take<float>((size_t)B * H);
-  g->chunk_rows = B < TOPK_CHUNK ? B : TOPK_CHUNK;
+  const bool fused_head = G.pilot_cols > 0 && B >= HEAD_FUSED_MIN_ROWS;
+  // the materialising path serves small batches and the flagged rows of the fused path: a few hundred logit rows are enough then
+  g->chunk_rows = fused_head ? HEAD_FUSED_MIN_ROWS : (B < TOPK_CHUNK ? B : TOPK_CHUNK);
   if (G.predictor && want_logits) {
     g->logits_ws = a.take<float>((size_t)g->chunk_rows * G.out_dim);
     g->topk_redo = a.take<int32_t>(g->chunk_rows);
+    g->fused_rows = fused_head ? (B < HEAD_ROW_CHUNK ? B : HEAD_ROW_CHUNK) : 0;
+    if (fused_head) {
+      const size_t R = g->fused_rows;
+      g->head_slots = ceil_div(G.out_dim, 256) * (GEMM_EPI_WARPS / 4);
+      g->pilot_logits = a.take<float>(R * HEAD_PILOT_COLS);
+      g->rowtau = a.take<float2>(R);
+      g->head_part = a.take<float>(R * g->head_slots);
+      g->head_cand = a.take<float2>(R * HEAD_CAND_CAP);
+      g->head_cnt = a.take<int32_t>(R), g->head_flagged = a.take<int32_t>(R), g->head_nflag = a.take<int32_t>(4);
+      g->redo_in = a.take<__nv_bfloat16>((size_t)g->chunk_rows * G.HH);
+      g->max_k = 1024;
+      g->redo_v = a.take<float>((size_t)g->chunk_rows * g->max_k), g->redo_i = a.take<int32_t>((size_t)g->chunk_rows * g->max_k);
+    }
   }
   *need = align_up(a.off, 256);
   return LLB_OK;
@@ -1112,6 +1297,11 @@ int llb_gin_pack_weights(const llb_gin_config* cfg, const llb_gin_weights* w, vo
   LLB_CUDA_OK(cp(G.head_ln_w, w->head_ln_w, G.HH));
   LLB_CUDA_OK(cp(G.head_ln_b, w->head_ln_b, G.HH));
   LLB_CUDA_OK(cp(G.head4_b, w->head4_b, G.HO));
+  if (G.pilot_cols > 0) {
+    gin_pilot_pack_kernel<<<G.pilot_cols, 256, 0, s>>>(w->head4_w, w->head4_b, G.HH, G.pilot_stride, G.pilot_cols, bf(G.pilot_w),
+                                                       reinterpret_cast<float*>(base + G.pilot_b));
+    LLB_CUDA_OK(cudaGetLastError());
+  }
   return LLB_OK;
 }
 
@@ -1247,19 +1437,78 @@ int llb_gin_predictor_topk(llb_gin* g, const float* c, int k, float* topk_prob, 
   cudaStream_t s = (cudaStream_t)stream;
   LLB_TRY(gin_trunk(g, c, s));
   LLB_TRY(gin_head_hidden(g, s));
-  for (int r0 = 0; r0 < g->B; r0 += g->chunk_rows) {
-    const int rows = g->B - r0 < g->chunk_rows ? g->B - r0 : g->chunk_rows;
-    LLB_TRY(gemm_bias_act(g->hz + (size_t)r0 * G.HH, G.HH, g->w<void>(G.head4_w), G.HH, g->w<float>(G.head4_b), g->logits_ws, G.out_dim,
-                          rows, G.out_dim, G.HH, LLB_ACT_NONE, true, s, &g->ctr));
-    ProfScope prof(LLB_PROF_GIN_TOPK, s);
-    launch_softmax_topk(g->logits_ws, rows, G.out_dim, G.out_dim, k, topk_prob + (size_t)r0 * k, topk_idx + (size_t)r0 * k, g->topk_redo, s);
+  g->ctr.slot = LLB_PROF_GIN_GEMM_HEAD;
+  // exact path over a range of head-input rows: materialise <= chunk_rows logit rows at a time, streaming softmax + top-k
+  auto materialise = [&](const __nv_bfloat16* in, int nrows, float* outv, int32_t* outi) -> int {
+    for (int r0 = 0; r0 < nrows; r0 += g->chunk_rows) {
+      const int rows = nrows - r0 < g->chunk_rows ? nrows - r0 : g->chunk_rows;
+      g->ctr.slot = LLB_PROF_GIN_GEMM_HEAD;
+      LLB_TRY(gemm_bias_act(in + (size_t)r0 * G.HH, G.HH, g->w<void>(G.head4_w), G.HH, g->w<float>(G.head4_b), g->logits_ws, G.out_dim, rows,
+                            G.out_dim, G.HH, LLB_ACT_NONE, true, s, &g->ctr));
+      ProfScope prof(LLB_PROF_GIN_TOPK, s);
+      launch_softmax_topk(g->logits_ws, rows, G.out_dim, G.out_dim, k, outv + (size_t)r0 * k, outi + (size_t)r0 * k, g->topk_redo, s);
+      LLB_CUDA_OK(cudaGetLastError());
+      g->launches += 3;
+    }
+    return LLB_OK;
+  };
+  g->head_flagged_rows = 0, g->head_fused_rows = 0;
+  if (g->fused_rows == 0 || k > g->max_k) return materialise(g->hz, g->B, topk_prob, topk_idx);
+  // ---- fused head + softmax + top-k (see EpiHeadTopk)
+  const long long r_need = ((long long)7 * k * HEAD_PILOT_COLS + G.out_dim - 1) / G.out_dim;
+  const int R = r_need < 4 ? 4 : (r_need > 32 ? 32 : (int)r_need);
+  for (int r0 = 0; r0 < g->B; r0 += g->fused_rows) {
+    const int rows = g->B - r0 < g->fused_rows ? g->B - r0 : g->fused_rows;
+    const __nv_bfloat16* in = g->hz + (size_t)r0 * G.HH;
+    LLB_CUDA_OK(cudaMemsetAsync(g->head_cnt, 0, (size_t)rows * 4, s));
+    LLB_CUDA_OK(cudaMemsetAsync(g->head_nflag, 0, 16, s));
+    g->ctr.slot = LLB_PROF_GIN_GEMM_HEAD;
+    LLB_TRY(gemm_bias_act(in, G.HH, g->w<void>(G.pilot_w), G.HH, g->w<float>(G.pilot_b), g->pilot_logits, HEAD_PILOT_COLS, rows, HEAD_PILOT_COLS,
+                          G.HH, LLB_ACT_NONE, true, s, &g->ctr));
+    {
+      ProfScope prof(LLB_PROF_GIN_TOPK, s);
+      gin_head_pilot_kernel<<<rows, 1024, 0, s>>>(g->pilot_logits, R, g->rowtau);
+    }
     LLB_CUDA_OK(cudaGetLastError());
-    g->launches += 3;
+    EpiHeadTopk eh{nullptr, 0, g->w<float>(G.head4_b), g->rowtau, g->head_part, g->head_slots, g->head_cand, g->head_cnt};
+    g->ctr.slot = LLB_PROF_GIN_GEMM_HEAD;
+    LLB_TRY((launch_gemm<256>(in, G.HH, g->w<void>(G.head4_w), G.HH, rows, G.out_dim, G.HH, eh, s, &g->ctr)));
+    note_kernel(LLB_KERN_HEAD_TOPK);
+    {
+      ProfScope prof(LLB_PROF_GIN_TOPK, s);
+      gin_head_select_kernel<<<rows, 256, 0, s>>>(g->head_part, g->head_slots, g->rowtau, g->head_cand, g->head_cnt, k, topk_prob + (size_t)r0 * k,
+                                                  topk_idx + (size_t)r0 * k, g->head_flagged, g->head_nflag);
+    }
+    LLB_CUDA_OK(cudaGetLastError());
+    g->launches += 2;
+    // the one host synchronisation of this entry: did any row fall outside the threshold scheme's guarantees?
+    int32_t nflag = 0;
+    LLB_CUDA_OK(cudaMemcpyAsync(&nflag, g->head_nflag, 4, cudaMemcpyDeviceToHost, s));
+    LLB_CUDA_OK(cudaStreamSynchronize(s));
+    g->head_flagged_rows += nflag, g->head_fused_rows += rows;
+    for (int f0 = 0; f0 < nflag; f0 += g->chunk_rows) {
+      const int fr = nflag - f0 < g->chunk_rows ? nflag - f0 : g->chunk_rows;
+      gin_gather_rows_kernel<<<fr, 128, 0, s>>>(in, g->head_flagged + f0, G.HH, g->redo_in);
+      LLB_CUDA_OK(cudaGetLastError());
+      LLB_TRY(materialise(g->redo_in, fr, g->redo_v, g->redo_i));
+      gin_scatter_topk_kernel<<<fr, 64, 0, s>>>(g->redo_v, g->redo_i, g->head_flagged + f0, k, topk_prob + (size_t)r0 * k, topk_idx + (size_t)r0 * k);
+      LLB_CUDA_OK(cudaGetLastError());
+      g->launches += 2;
+    }
   }
   return LLB_OK;
 }
 
 int64_t llb_gin_launch_count(const llb_gin* g) { return g ? g->launches + g->ctr.launches : 0; }
+
+int64_t llb_gin_stat(const llb_gin* g, int which) {
+  if (!g) return -1;
+  switch (which) {
+    case LLB_GIN_STAT_HEAD_FUSED_ROWS: return g->head_fused_rows;
+    case LLB_GIN_STAT_HEAD_FLAGGED_ROWS: return g->head_flagged_rows;
+    default: return -1;
+  }
+}
 
 int llb_softmax_topk(const float* logits, int rows, int W, int ld, int k, float* topk_prob, int32_t* topk_idx, int32_t* scratch,
                      llb_stream_t stream) {

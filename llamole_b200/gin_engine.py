@@ -166,5 +166,9 @@ class GinEngine:
                                                         _cabi.stream_ptr()), "llb_gin_predictor_topk")
         return probs, idx
 
+    def head_stats(self) -> dict:
+        """Rows of the last predictor_topk call that used the fused head kernel / that fell back to the exact path."""
+        return {"fused_rows": int(self.lib.llb_gin_stat(self.handle, 0)), "flagged_rows": int(self.lib.llb_gin_stat(self.handle, 1))}
+
     def launch_count(self) -> int:
         return int(self.lib.llb_gin_launch_count(self.handle))

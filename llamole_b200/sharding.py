@@ -52,15 +52,20 @@ def split_graph_batch(x, edge_index, edge_attr, batch, g0: int, g1: int):
     return x[idx], edge_index[:, e_sel] - n0, edge_attr[e_sel], batch[idx] - g0
 
 
-def all_gather_rows(t: torch.Tensor, group=None) -> torch.Tensor:
-    """All-gather along dim 0 for per-rank tensors whose first dimension may differ (pads to the max)."""
+def all_gather_rows(t: torch.Tensor, group=None, sizes: Optional[Sequence[int]] = None) -> torch.Tensor:
+    """All-gather along dim 0 for per-rank tensors whose first dimension may differ (pads to the max).  `sizes` = every
+    rank's row count when the caller knows it (contiguous shards): saves the size exchange and its host synchronisation."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return t
     world = dist.get_world_size(group)
-    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
-    sizes = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(sizes, n, group=group)
-    sizes = [int(s.item()) for s in sizes]
+    if sizes is None:
+        n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+        got = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(got, n, group=group)
+        sizes = [int(s.item()) for s in got]
+    sizes = list(sizes)
+    if len(sizes) != world or sizes[dist.get_rank(group)] != t.shape[0]:
+        raise ValueError(f"all_gather_rows: sizes {sizes} do not describe this rank's {t.shape[0]} rows")
     m = max(sizes)
     pad = t.new_zeros((m,) + tuple(t.shape[1:]))
     pad[: t.shape[0]] = t
@@ -69,24 +74,41 @@ def all_gather_rows(t: torch.Tensor, group=None) -> torch.Tensor:
     return torch.cat([o[:s] for o, s in zip(outs, sizes)], dim=0)
 
 
-def pack_graphs(X: torch.Tensor, E: torch.Tensor, n: torch.Tensor) -> torch.Tensor:
+_TRIU_CACHE = {}
+
+
+def _triu(N: int, device) -> torch.Tensor:
+    """Flat indices i * N + j of the upper triangle (with diagonal) of an N x N matrix, cached per (N, device)."""
+    key = (N, str(device))
+    if key not in _TRIU_CACHE:
+        iu = torch.triu_indices(N, N, device=device)
+        _TRIU_CACHE[key] = iu[0] * N + iu[1]
+    return _TRIU_CACHE[key]
+
+
+def pack_graphs(X: torch.Tensor, E: torch.Tensor, n: torch.Tensor, check: bool = True) -> torch.Tensor:
     """Compact wire format of sampled graphs: per molecule one row of
     `2 + N + N(N+1)/2` bytes = node count (little-endian u16) | atom classes + 1 | upper triangle (with diagonal) of
     the bond classes + 1, so the masked value -1 travels as 0.  1327 B per molecule at N=50 instead of 20.4 KB of int64.
-    E must be symmetric (the sampler mirrors the upper triangle, diffusion_utils.py:316-349)."""
+    E must be symmetric (the sampler mirrors the upper triangle, diffusion_utils.py:316-349).  Any integer dtype (the engine's
+    int8 state or the int64 tensors of generate_graphs); `check=False` skips the symmetry / range validation, which costs three
+    host synchronisations (for tensors that come straight from the sampler)."""
     B, N = X.shape
     if E.shape != (B, N, N) or n.shape != (B,):
         raise ValueError(f"pack_graphs: X {tuple(X.shape)}, E {tuple(E.shape)}, n {tuple(n.shape)}")
-    if not torch.equal(E, E.transpose(1, 2)):
-        raise ValueError("pack_graphs: E is not symmetric")
-    iu = torch.triu_indices(N, N, device=E.device)
-    lo, hi = int(min(X.min(), E.min())) if B else 0, int(max(X.max(), E.max())) if B else 0
-    if lo < -1 or hi > 254:
-        raise ValueError("pack_graphs: classes must lie in [-1, 254]")
-    nn_ = n.to(torch.int64)
-    head = torch.stack([nn_ & 0xFF, nn_ >> 8], dim=1)
-    row = torch.cat([head, X.to(torch.int64) + 1, E[:, iu[0], iu[1]].to(torch.int64) + 1], dim=1)
-    return row.to(torch.uint8)
+    if check and B:
+        if not torch.equal(E, E.transpose(1, 2)):
+            raise ValueError("pack_graphs: E is not symmetric")
+        lo, hi = int(min(X.min(), E.min())), int(max(X.max(), E.max()))
+        if lo < -1 or hi > 254:
+            raise ValueError("pack_graphs: classes must lie in [-1, 254]")
+    nn_ = n.to(torch.int32)
+    row = torch.empty((B, 2 + N + N * (N + 1) // 2), dtype=torch.uint8, device=X.device)
+    row[:, 0] = (nn_ & 0xFF).to(torch.uint8)
+    row[:, 1] = (nn_ >> 8).to(torch.uint8)
+    row[:, 2:2 + N] = (X.to(torch.int16) + 1).to(torch.uint8)
+    row[:, 2 + N:] = (E.reshape(B, N * N).index_select(1, _triu(N, E.device)).to(torch.int16) + 1).to(torch.uint8)
+    return row
 
 
 def unpack_graphs(wire: torch.Tensor, N: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
@@ -94,15 +116,14 @@ def unpack_graphs(wire: torch.Tensor, N: int) -> Tuple[torch.Tensor, torch.Tenso
     B = wire.shape[0]
     if wire.shape[1] != 2 + N + N * (N + 1) // 2:
         raise ValueError(f"unpack_graphs: row of {wire.shape[1]} bytes does not match N={N}")
-    w = wire.to(torch.int64)
-    n = w[:, 0] | (w[:, 1] << 8)
-    X = w[:, 2:2 + N] - 1
-    iu = torch.triu_indices(N, N, device=wire.device)
-    E = torch.empty((B, N, N), dtype=torch.int64, device=wire.device)
-    tri = w[:, 2 + N:] - 1
-    E[:, iu[0], iu[1]] = tri
-    E[:, iu[1], iu[0]] = tri
-    return X, E, n
+    n = wire[:, 0].to(torch.int64) | (wire[:, 1].to(torch.int64) << 8)
+    X = wire[:, 2:2 + N].to(torch.int64) - 1
+    tri = wire[:, 2 + N:].to(torch.int64) - 1
+    flat = _triu(N, wire.device)
+    E = torch.empty((B, N * N), dtype=torch.int64, device=wire.device)
+    E[:, flat] = tri
+    E[:, (flat % N) * N + flat // N] = tri
+    return X, E.view(B, N, N), n
 
 
 def _comm_device(group=None) -> torch.device:
@@ -140,9 +161,10 @@ def sample_graphs_sharded(generate_fn: Callable, properties: torch.Tensor, text_
         n = torch.zeros((0,), dtype=torch.int64, device=dev)
     if world == 1:
         return X, E, n
+    sizes = [b - a for a, b in (shard_range(properties.shape[0], r, world) for r in range(world))]
     if wire == "full":
-        return all_gather_rows(X, group), all_gather_rows(E, group), all_gather_rows(n, group)
-    Xg, Eg, ng = unpack_graphs(all_gather_rows(pack_graphs(X, E, n), group), X.shape[1])
+        return all_gather_rows(X, group, sizes), all_gather_rows(E, group, sizes), all_gather_rows(n, group, sizes)
+    Xg, Eg, ng = unpack_graphs(all_gather_rows(pack_graphs(X, E, n, check=False), group, sizes), X.shape[1])
     return Xg.to(X.dtype), Eg.to(E.dtype), ng.to(n.dtype)
 
 
