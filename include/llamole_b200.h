@@ -81,17 +81,11 @@ int llb_gemm_bf16(const void* A, int lda, const void* W, int ldw, const float* b
 
 /* Fused tail of a GraphDiT block half (transformer.py:143-144):
  *   x[r,:] += gate[g] * ( LayerNorm(A[r,:] . W^T + bias) * (1 + scale[g]) + shift[g] ),  g = row_group[r]
- * LayerNorm over the N output columns (eps 1e-5, no affine) on the fp32 accumulators; x (M, ldx) fp32 is updated
- * in place and xb (M, ldxb) receives its bf16 copy (the next GEMM's operand; must not alias A).  shift / scale /
- * gate point at (groups, mod_ld) fp32 matrices.  N must be 256, 512, 768 or 1024 (one CTA per 256 columns, one
- * thread-block cluster per 128-row tile); other widths return LLB_ERR_INVALID. */
-int llb_gemm_ln_residual(const void* A, int lda, const void* W, int ldw, const float* bias, const int32_t* row_group,
-                         const float* shift, const float* scale, const float* gate, int mod_ld, float* x, int ldx,
-                         void* xb, int ldxb, int M, int N, int K, llb_stream_t stream);
-/* Same operation for N = 1024 on CTA pairs (tcgen05.mma.cta_group::2): four pairs share a 256-row block and exchange
- * the LayerNorm statistics through `workspace` (llb_gemm_ln_workspace_bytes bytes, 128-byte aligned, owned by the caller,
- * not shared with a concurrent launch).  The faster of the two for K >= 1024; the GraphDiT sampler uses it for both
- * block halves. */
+ * LayerNorm over the N = 1024 output columns (eps 1e-5, no affine) on the fp32 accumulators; x (M, ldx) fp32 is updated in
+ * place and xb (M, ldxb) receives its bf16 copy (the next GEMM's operand; must not alias A).  shift / scale / gate point at
+ * (groups, mod_ld) fp32 matrices.  Runs on CTA pairs (tcgen05.mma.cta_group::2): four pairs share a 256-row block and exchange
+ * the LayerNorm statistics through `workspace` (llb_gemm_ln_workspace_bytes bytes, 128-byte aligned, owned by the caller, not
+ * shared with a concurrent launch).  Other widths return LLB_ERR_INVALID (the sampler then uses GEMM + row kernel). */
 int llb_gemm_ln_workspace_bytes(size_t* bytes);
 int llb_gemm_ln_residual_ws(const void* A, int lda, const void* W, int ldw, const float* bias, const int32_t* row_group,
                             const float* shift, const float* scale, const float* gate, int mod_ld, float* x, int ldx,

@@ -69,7 +69,6 @@ SIGNATURES = {
     "llb_profile_slot_name": (C.c_char_p, [_I]),
     "llb_kernel_launches": (C.c_int64, [_I]),
     "llb_gemm_bf16": (_I, [_P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
-    "llb_gemm_ln_residual": (_I, [_P, _I, _P, _I, _P, _P, _P, _P, _P, _I, _P, _I, _P, _I, _I, _I, _I, _P]),
     "llb_gemm_ln_workspace_bytes": (_I, [C.POINTER(_SZ)]),
     "llb_gemm_ln_residual_ws": (_I, [_P, _I, _P, _I, _P, _P, _P, _P, _P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _SZ, _P]),
     "llb_dit_packed_bytes": (_I, [C.POINTER(DitConfig), C.POINTER(_SZ)]),

@@ -303,13 +303,12 @@ static int dit_forward(llb_dit* h, int t, cudaStream_t s) {
   const int ldh = (D + 1) * H;
   LLB_TRY(gemm_bias_act(h->cvec, H, h->w<void>(L.ada0_w), H, h->w<float>(L.ada0_b), h->hid, ldh, B + 1, ldh, H, LLB_ACT_SILU, false, s, ctr));
   // the D modulation linears depend only on the condition: ONE launch grouped along N (group l reads hid[:, l H : (l+1) H],
-  // its 6H x H weight is rows [l 6H, (l+1) 6H) of the stacked operand); mod is (B+1, D, 6H).  LLB_ADALN_GROUPED=0: D launches.
-  static const bool adaln_split = getenv("LLB_ADALN_GROUPED") && getenv("LLB_ADALN_GROUPED")[0] == '0';
+  // its 6H x H weight is rows [l 6H, (l+1) 6H) of the stacked operand); mod is (B+1, D, 6H).
   const int ldm = D * 6 * H;
   // the stacked operand needs the D weights (and biases) back to back in the blob: true whenever 6 H H 2 and 6 H 4 bytes are
   // multiples of the blob's 256-byte alignment; checked rather than assumed
   const bool stacked = D == 1 || (L.ada2_w[1] - L.ada2_w[0] == (size_t)6 * H * H * 2 && L.ada2_b[1] - L.ada2_b[0] == (size_t)6 * H * 4);
-  if (!adaln_split && stacked && (6 * H) % 256 == 0) {
+  if (stacked && (6 * H) % 256 == 0) {
     GemmGroups grp;
     grp.group_n = 6 * H, grp.group_k = H;
     LLB_TRY(gemm_bias_act(h->hid, ldh, h->w<void>(L.ada2_w[0]), H, h->w<float>(L.ada2_b[0]), h->mod, ldm, B + 1, ldm, H, LLB_ACT_SOFTSIGN, true, s,
@@ -330,26 +329,22 @@ static int dit_forward(llb_dit* h, int t, cudaStream_t s) {
   static const bool ln_env_set = getenv("LLB_FUSED_LN") != nullptr;
   const bool latency_regime = !ln_env_set && M < 2048;
   const bool fused_ln = gemm_ln_supported(H, H) && gemm_ln_supported(H, F) && gemm_ln_enabled() && !latency_regime;
-  // LLB_FUSED_LN: 0 = GEMM + row kernel; 1 = fused, 4-CTA cluster kernel (projection only: with K = 4 H its single-CTA
-  // main loop loses more than the row kernel costs); 2 = cluster kernel for both halves; 3 (default) = fused on the
-  // CTA-pair main loop for both halves when H = 1024, else as 1.
-  // LLB_ATTN: 1 = mma.sync kernel with register-staged loads; 3 (default) = the same with TMA-delivered operands;
-  // 2 = tcgen05 kernel (two heads per 128-row tile, P in tensor memory; needs an even head count)
+  // LLB_FUSED_LN=0: GEMM + row kernel everywhere; default: both block halves fused on the CTA-pair kernel when H = 1024
+  // (other widths have no fused kernel: a full row must fit four pairs' tensor memory).
+  // LLB_ATTN=2: tcgen05 attention (two heads per 128-row tile, P in tensor memory; needs an even head count); default: mma.sync
+  // attention fed by TMA.
   static int attn_env = -1;
   if (attn_env < 0) {
     const char* v = getenv("LLB_ATTN");
-    int mode = (v && v[0] >= '1' && v[0] <= '3') ? v[0] - '0' : LLB_ATTN_DEFAULT;
+    int mode = (v && v[0] == '2') ? 2 : 3;
     if (mode == 2 && cudaFuncSetAttribute(dit_attention_umma4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT4_SMEM) != cudaSuccess) {
       (void)cudaGetLastError();
-      mode = 1;
+      mode = 3;
     }
     attn_env = mode;
   }
-  const bool attn_umma = attn_env == 2 && L.heads % 2 == 0 && L.N <= 64;
-  const bool attn_tma = attn_env == 3 && L.N <= 64;
-  const int ln_mode = gemm_ln_mode();
-  const bool fused_pair = fused_ln && (ln_mode == 3 || ln_mode == 4) && H == 4 * GLN_BN;   // 4 = pair kernel, projection only
-  const bool fused_fc2 = ln_mode == 2 || (fused_pair && ln_mode == 3);
+  const bool attn_umma = attn_env == 2 && L.heads % 2 == 0;
+  const bool fused_pair = fused_ln;
   const size_t ln_sync_bytes = gemm_ln_pair_workspace_bytes();
   for (int l = 0; l < D; ++l) {
     const float* mod = h->mod + (size_t)l * 6 * H;   // row stride ldm
@@ -361,20 +356,15 @@ static int dit_forward(llb_dit* h, int t, cudaStream_t s) {
     LLB_TRY((launch_gemm<256>(h->xb, H, h->w<void>(L.qkv_w[l]), H, share0 ? Mtok : M, 3 * H, H, eq, s, ctr)));
     {
       const int seqs = (share0 ? 1 : h->passes) * B;
-      if (attn_umma || attn_tma) {
-        CUtensorMap tmQKV;
-        LLB_TRY(make_tensor_map_2d(&tmQKV, h->qkv, 2, seqs / B * Mtok, 3 * H, 3 * H, DIT_DH, 64, 128));
-        ProfScope prof(LLB_PROF_ATTENTION, s);
-        if (attn_umma) {
-          const int units = seqs * (L.heads / 2);
-          dit_attention_umma4_kernel<<<units < num_sms() ? units : num_sms(), ATT4_THREADS, ATT4_SMEM, s>>>(tmQKV, h->attn, h->mol_off, B, Mtok, H,
-                                                                                                            L.heads, units);
-        } else {
-          dit_attention_tma_kernel<<<(unsigned)(seqs * L.heads), 128, 0, s>>>(tmQKV, h->attn, h->mol_off, B, Mtok, H, L.heads);
-        }
+      CUtensorMap tmQKV;
+      LLB_TRY(make_tensor_map_2d(&tmQKV, h->qkv, 2, seqs / B * Mtok, 3 * H, 3 * H, DIT_DH, 64, 128));
+      ProfScope prof(LLB_PROF_ATTENTION, s);
+      if (attn_umma) {
+        const int units = seqs * (L.heads / 2);
+        dit_attention_umma4_kernel<<<units < num_sms() ? units : num_sms(), ATT4_THREADS, ATT4_SMEM, s>>>(tmQKV, h->attn, h->mol_off, B, Mtok, H,
+                                                                                                          L.heads, units);
       } else {
-        ProfScope prof(LLB_PROF_ATTENTION, s);
-        dit_attention_kernel<<<(unsigned)(seqs * L.heads), 128, 0, s>>>(h->qkv, h->attn, h->mol_off, B, Mtok, H, L.heads);
+        dit_attention_tma_kernel<<<(unsigned)(seqs * L.heads), 128, 0, s>>>(tmQKV, h->attn, h->mol_off, B, Mtok, H, L.heads);
       }
     }
     LLB_CUDA_OK(cudaGetLastError());
@@ -393,8 +383,7 @@ static int dit_forward(llb_dit* h, int t, cudaStream_t s) {
         GemmLnArgs fp = f;
         const int rows = share0 ? Mtok : M;
         fp.row_group = f.row_group + (size_t)part * Mtok, fp.x = f.x + (size_t)part * Mtok * H, fp.xb = f.xb + (size_t)part * Mtok * H;
-        if (fused_pair) LLB_TRY(launch_gemm_ln_pair(h->attn, H, h->w<void>(L.proj_w[l]), H, rows, H, H, fp, h->ln_sync, ln_sync_bytes, s, ctr));
-        else LLB_TRY(launch_gemm_ln(h->attn, H, h->w<void>(L.proj_w[l]), H, rows, H, H, fp, s, ctr));
+        LLB_TRY(launch_gemm_ln_pair(h->attn, H, h->w<void>(L.proj_w[l]), H, rows, H, H, fp, h->ln_sync, ln_sync_bytes, s, ctr));
       }
     } else {
       LLB_TRY(gemm_bias_act(h->attn, H, h->w<void>(L.proj_w[l]), H, h->w<float>(L.proj_b[l]), h->y, H, M, H, H, LLB_ACT_NONE, false, s, ctr));
@@ -405,10 +394,9 @@ static int dit_forward(llb_dit* h, int t, cudaStream_t s) {
     ctr->slot = LLB_PROF_GEMM_FC1;
     LLB_TRY(gemm_bias_act(h->xb, H, h->w<void>(L.fc1_w[l]), H, h->w<float>(L.fc1_b[l]), h->hbuf, F, M, F, H, LLB_ACT_GELU, false, s, ctr));
     ctr->slot = LLB_PROF_GEMM_FC2;
-    if (fused_ln && fused_fc2) {
+    if (fused_pair) {
       f.bias = h->w<float>(L.fc2_b[l]), f.shift = mod + 3 * H, f.scale = mod + 4 * H, f.gate = mod + 5 * H;
-      if (fused_pair) LLB_TRY(launch_gemm_ln_pair(h->hbuf, F, h->w<void>(L.fc2_w[l]), F, M, H, F, f, h->ln_sync, ln_sync_bytes, s, ctr));
-      else LLB_TRY(launch_gemm_ln(h->hbuf, F, h->w<void>(L.fc2_w[l]), F, M, H, F, f, s, ctr));
+      LLB_TRY(launch_gemm_ln_pair(h->hbuf, F, h->w<void>(L.fc2_w[l]), F, M, H, F, f, h->ln_sync, ln_sync_bytes, s, ctr));
     } else {
       // latency regime: K = F is cut into LLB_DIT_SPLITK slices that run as groups of one launch (4x the CTAs streaming the
       // weights, a quarter of the k-blocks each); the row kernel adds the fp32 partial products in slice order

@@ -111,141 +111,10 @@ __device__ __forceinline__ void mma_bf16_16816(float* c, uint32_t a0, uint32_t a
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-__global__ void __launch_bounds__(128) dit_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
-                                                            const int32_t* __restrict__ mol_off, int B, int Mtok, int H, int heads) {
-  __shared__ __align__(16) __nv_bfloat16 sQ[64 * ATT_LD];
-  __shared__ __align__(16) __nv_bfloat16 sK[64 * ATT_LD];
-  __shared__ __align__(16) __nv_bfloat16 sV[64 * ATT_LD];
-  // heads vary fastest across the grid: the 16 CTAs that read the q/k/v head slices of one sequence's rows (6 KB
-  // contiguous per token) run together, which keeps the DRAM pages they share open
-  const int head = blockIdx.x % heads;
-  const int seq = blockIdx.x / heads;  // pass * B + molecule
-  const int b = seq % B, pass = seq / B;
-  const int row0 = pass * Mtok + mol_off[b];
-  const int n = mol_off[b + 1] - mol_off[b];
-  if (n == 0) return;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int ld = 3 * H;
-  const int npad = (n + 15) & ~15;
-  // load q, k, v head slices: thread -> (row tid/8 + 16 it, 16-byte piece tid%8); rows in [n, npad) are zero
-  {
-    const int r0l = tid >> 3, ch = tid & 7;
-    const __nv_bfloat16* src = qkv + (size_t)row0 * ld + head * DIT_DH + ch * 8;
-    uint4 v[3][4];
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int r = r0l + 16 * it;
-#pragma unroll
-      for (int mat = 0; mat < 3; ++mat)
-        v[mat][it] = r < n ? __ldg(reinterpret_cast<const uint4*>(src + (size_t)r * ld + mat * H)) : make_uint4(0, 0, 0, 0);
-    }
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int r = r0l + 16 * it;
-      if (r < npad) {
-        *reinterpret_cast<uint4*>(sQ + r * ATT_LD + ch * 8) = v[0][it];
-        *reinterpret_cast<uint4*>(sK + r * ATT_LD + ch * 8) = v[1][it];
-        *reinterpret_cast<uint4*>(sV + r * ATT_LD + ch * 8) = v[2][it];
-      }
-    }
-  }
-  __syncthreads();
-  if (warp * 16 >= n) return;
-  const int ntiles = npad >> 3;  // key tiles of 8
-  // ---- S = Q K^T
-  float s[8][4];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-#pragma unroll
-  for (int ks = 0; ks < 4; ++ks) {
-    uint32_t a0, a1, a2, a3;
-    ldsm_x4(smem_u32(sQ + (warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * ATT_LD + ks * 16 + (lane >> 4) * 8), a0, a1, a2, a3);
-#pragma unroll
-    for (int jp = 0; jp < 4; ++jp) {
-      if (jp * 2 < ntiles) {
-        uint32_t b0, b1, b2, b3;
-        ldsm_x4(smem_u32(sK + (jp * 16 + (lane & 7) + (lane >> 4) * 8) * ATT_LD + ks * 16 + ((lane >> 3) & 1) * 8), b0, b1, b2, b3);
-        mma_bf16_16816(s[2 * jp], a0, a1, a2, a3, b0, b1);
-        mma_bf16_16816(s[2 * jp + 1], a0, a1, a2, a3, b2, b3);
-      }
-    }
-  }
-  // ---- softmax over keys < n (rows g and g+8 of this warp's 16)
-  const int t4 = lane & 3;
-  float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int key = j * 8 + t4 * 2 + e;
-      if (key >= n) s[j][e] = s[j][2 + e] = -INFINITY;
-      m0 = fmaxf(m0, s[j][e]);
-      m1 = fmaxf(m1, s[j][2 + e]);
-    }
-  }
-  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
-  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
-  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-  float l0 = 0.f, l1 = 0.f;
-  uint32_t p[8][2];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float e0 = ex2_approx(s[j][0] - m0), e1 = ex2_approx(s[j][1] - m0);   // MUFU.EX2 alone: exp2f adds a range fix-up per call
-    const float e2 = ex2_approx(s[j][2] - m1), e3 = ex2_approx(s[j][3] - m1);
-    l0 += e0 + e1;
-    l1 += e2 + e3;
-    p[j][0] = pack_bf16x2(e0, e1);
-    p[j][1] = pack_bf16x2(e2, e3);
-  }
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-  // ---- O = P V
-  float o[8][4];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
-#pragma unroll
-  for (int ks = 0; ks < 4; ++ks) {
-    if (ks * 16 < npad) {
-      const uint32_t a0 = p[2 * ks][0], a1 = p[2 * ks][1], a2 = p[2 * ks + 1][0], a3 = p[2 * ks + 1][1];
-#pragma unroll
-      for (int dp = 0; dp < 4; ++dp) {
-        uint32_t b0, b1, b2, b3;
-        ldsm_x4_t(smem_u32(sV + (ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * ATT_LD + dp * 16 + (lane >> 4) * 8), b0, b1, b2, b3);
-        mma_bf16_16816(o[2 * dp], a0, a1, a2, a3, b0, b1);
-        mma_bf16_16816(o[2 * dp + 1], a0, a1, a2, a3, b2, b3);
-      }
-    }
-  }
-  const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
-  const int g = lane >> 2;
-  // stage the warp's 16 x 64 output tile in its own (already consumed) Q rows, then write 16-byte pieces so that
-  // 8 lanes cover one 128-byte row segment (the direct fragment layout would issue 16-byte-per-row stores)
-  __nv_bfloat16* sO = sQ + warp * 16 * ATT_LD;
-  __syncwarp();
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int col = j * 8 + t4 * 2;
-    *reinterpret_cast<uint32_t*>(sO + g * ATT_LD + col) = pack_bf16x2(o[j][0] * inv0, o[j][1] * inv0);
-    *reinterpret_cast<uint32_t*>(sO + (g + 8) * ATT_LD + col) = pack_bf16x2(o[j][2] * inv1, o[j][3] * inv1);
-  }
-  __syncwarp();
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int p = lane + 32 * i;
-    const int r = p >> 3, ch = p & 7;
-    const int grow = warp * 16 + r;
-    if (grow < n)
-      *reinterpret_cast<uint4*>(out + (size_t)(row0 + grow) * H + head * DIT_DH + ch * 8) = *reinterpret_cast<const uint4*>(sO + r * ATT_LD + ch * 8);
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
-// The same attention with the operands delivered by TMA (LLB_ATTN=3).  The kernel above spends a third of its
-// shared-memory wavefronts on getting q/k/v INTO shared memory (12 LDG.128 + 12 STS.128 per thread, through registers);
-// here one thread issues three 64 x 64 box loads of the qkv matrix (128-byte swizzle, so ldmatrix stays conflict-free
+// Default attention kernel: operands delivered by TMA.  (A first version staged q/k/v through registers -- 12 LDG.128 + 12
+// STS.128 per thread, a third of its shared-memory wavefronts -- and ran 15.8 instead of 12.5 ms/step; removed in round 2.)
+// One thread issues three 64 x 64 box loads of the qkv matrix (128-byte swizzle, so ldmatrix stays conflict-free
 // without padding) and the CTA waits on one mbarrier.  Rows past the end of the sequence hold the next sequence's
 // tokens (or zeros past the end of the matrix): keys >= n are masked to -inf exactly as before, so they contribute
 // p = 0 times a finite value; queries >= n are never stored.

@@ -578,7 +578,6 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 int make_tensor_map_2d(CUtensorMap* out, const void* ptr, int elem_bytes, int rows, int cols, int ld_elems, int box_cols,
                        int box_rows, int swizzle_bytes);
 
-bool gemm_pair_enabled();   // LLB_GEMM_PAIR=0 forces the single-CTA kernel (debug / A-B comparison)
 
 // Grouped along N (group_n > 0): output columns [g group_n, (g+1) group_n) are A[:, g group_k : g group_k + K] . W[g group_n ..]^T,
 // i.e. G independent linears that share their rows, with their (N_g, K) weights stacked and their inputs side by side --
@@ -626,7 +625,7 @@ int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, in
   static bool configured[4] = {false, false, false, false};  // per template instantiation
   // CTA-pair kernel: wide problems whose 256 x 256 pair-tiles fill the machine
   const int pair_tiles = ceil_div(M, 2 * GEMM_BM) * ceil_div(N, 256);
-  const bool use_pair = BN == 256 && gemm_pair_enabled() && pair_tiles >= num_sms() / 2 && grp.group_n % 256 == 0;
+  const bool use_pair = BN == 256 && pair_tiles >= num_sms() / 2 && grp.group_n % 256 == 0;
   if (use_pair) {
     CUtensorMap tmBh;
     LLB_TRY(make_tensor_map_2d(&tmBh, W, 2, w_rows, w_cols, ldw, GEMM_BK, 128, 128));

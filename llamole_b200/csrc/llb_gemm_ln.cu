@@ -1,4 +1,4 @@
-// Cluster GEMM with the LayerNorm / adaLN-modulate / gate / residual tail fused into the epilogue (see llb_gemm_ln.cuh).
+// CTA-pair GEMMs with a LayerNorm tail fused into the epilogue: GraphDiT block tails (N = 1024) and GIN layer tails (N = 768 / 1024); see llb_gemm_ln.cuh.
 #include <stdlib.h>
 
 #include <atomic>
@@ -20,48 +20,10 @@ __device__ int g_gln_exp = 0;                  // knock-outs: 1 no x store, 2 no
 #define GLN_TRACE(tile_idx, slot, value) do { } while (0)
 #endif
 
-struct GlnSmem {
-  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;            // 16 KB
-  static constexpr int B_BYTES = GLN_BN * GEMM_BK * 2;             // 32 KB
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int XSTG_PER_WARP = 32 * 32 * 4;                // 32 rows x 32 fp32 (128-byte rows, TMA 128B swizzle)
-  static constexpr int XBSTG_PER_WARP = 32 * 32 * 2;               // 32 rows x 32 bf16 (64-byte rows, TMA 64B swizzle)
-  static constexpr int MOD_STAGE_FLOATS = GLN_MAX_GROUPS * 2 * GLN_BN;   // per group: gate*(1+scale), gate*shift
-  static constexpr int OFF_XSTG = GLN_STAGES * STAGE_BYTES;
-  static constexpr int OFF_XBSTG = OFF_XSTG + GEMM_EPI_WARPS * XSTG_PER_WARP;
-  static constexpr int OFF_MOD = OFF_XBSTG + GEMM_EPI_WARPS * XBSTG_PER_WARP;       // [2][groups][2][256] fp32
-  static constexpr int OFF_BIAS = OFF_MOD + 2 * MOD_STAGE_FLOATS * 4;
-  static constexpr int OFF_STATS = OFF_BIAS + GLN_BN * 4;                           // [2][CL][128] float2 (received)
-  static constexpr int OFF_SEND = OFF_STATS + 2 * GLN_MAX_CL * GEMM_BM * 8;         // [2][128] float2 (this CTA's row sums)
-  static constexpr int OFF_PART = OFF_SEND + 2 * GEMM_BM * 8;                       // [2 halves][128] float2
-  static constexpr int OFF_ROWINFO = OFF_PART + 2 * GEMM_BM * 8;                    // [2][128] int2 {local group, group}
-  static constexpr int OFF_GLIST = OFF_ROWINFO + 2 * GEMM_BM * 8;                   // [2][8] int: 4 group ids, count
-  static constexpr int OFF_BARS = OFF_GLIST + 64;
-  static constexpr int TOTAL = OFF_BARS + 256 + 1024;                               // + alignment slack
-};
-static_assert(GlnSmem::TOTAL <= 232448, "gemm_ln shared memory exceeds the 227 KB per-CTA limit");
-
 __device__ __forceinline__ uint32_t cluster_rank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
-}
-__device__ __forceinline__ void cluster_barrier() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_t cta) {
-  uint32_t remote;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_smem_addr), "r"(cta));
-  return remote;
-}
-// Bulk copy of this CTA's shared memory into a peer's (distributed shared memory); the peer's mbarrier receives the
-// byte count.  Data and signal travel through the async proxy, so no cluster-scope fence (a MEMBAR.GPU that would
-// wait for the epilogue's outstanding global stores) is needed on either side.
-__device__ __forceinline__ void dsmem_bulk_copy(uint32_t remote_dst, uint32_t local_src, uint32_t bytes, uint32_t remote_bar) {
-  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(remote_dst), "r"(local_src), "r"(bytes), "r"(remote_bar)
-               : "memory");
 }
 // One instruction pulls a whole (rows x cols) box of a tensor into L2.
 __device__ __forceinline__ void l2_prefetch_tile(const CUtensorMap* map, int c0, int c1) {
@@ -97,98 +59,6 @@ struct GlnPass2 {
   float rstd, nmr;
   int trace_tile;        // debug builds only
 };
-
-// normalise + modulate + gate -> staging transpose -> residual add in coalesced layout -> TMA stores of x and xb.
-// Global stores go through the TMA (bulk async) path: generic STG from 8 warps tops out near 12 bytes/clk/SM (bounded
-// by the outstanding-store window), which made this phase the critical path of the whole tile.
-template <bool STAGED>
-__device__ __forceinline__ void gln_pass2(const GlnPass2& a, const CUtensorMap* tmX, const CUtensorMap* tmXb, float4 (&res)[8], int lane) {
-  const int sl = lane & 7, rsub = lane >> 3;
-  const uint32_t wr = a.xstg + lane * 128;
-  float v[32];
-#ifdef LLB_GEMM_TRACE
-  long long tt0 = 0, tt1 = 0, tt2 = 0, tt3 = 0;
-#endif
-#pragma unroll 1
-  for (int c = 0; c < GLN_BN / 2; c += 32) {
-#ifdef LLB_GEMM_TRACE
-    const long long k0 = clock64();
-#endif
-    tmem_ld32(a.t_row + c, v);
-    tmem_ld_wait();
-#ifdef LLB_GEMM_TRACE
-    const long long k1 = clock64();
-#endif
-#pragma unroll
-    for (int p = 0; p < 8; ++p) {
-      const float4 b = lds128(a.bias_s + (c + 4 * p) * 4);
-      float4 s1, sh;
-      if (STAGED) {
-        s1 = lds128(a.mod_s + (c + 4 * p) * 4);
-        sh = lds128(a.mod_s + (GLN_BN + c + 4 * p) * 4);
-      } else {
-        const float4 gt = __ldg(reinterpret_cast<const float4*>(a.g_gate + c + 4 * p));
-        s1 = __ldg(reinterpret_cast<const float4*>(a.g_scale + c + 4 * p));
-        sh = __ldg(reinterpret_cast<const float4*>(a.g_shift + c + 4 * p));
-        s1.x = (1.0f + s1.x) * gt.x, s1.y = (1.0f + s1.y) * gt.y, s1.z = (1.0f + s1.z) * gt.z, s1.w = (1.0f + s1.w) * gt.w;
-        sh.x *= gt.x, sh.y *= gt.y, sh.z *= gt.z, sh.w *= gt.w;
-      }
-      v[4 * p] = fmaf(fmaf(v[4 * p] + b.x, a.rstd, a.nmr), s1.x, sh.x);
-      v[4 * p + 1] = fmaf(fmaf(v[4 * p + 1] + b.y, a.rstd, a.nmr), s1.y, sh.y);
-      v[4 * p + 2] = fmaf(fmaf(v[4 * p + 2] + b.z, a.rstd, a.nmr), s1.z, sh.z);
-      v[4 * p + 3] = fmaf(fmaf(v[4 * p + 3] + b.w, a.rstd, a.nmr), s1.w, sh.w);
-    }
-    // the staging tiles are free once the previous chunk's TMA stores have read them
-    if (elect_one()) bulk_wait_read<0>();
-    __syncwarp();
-#pragma unroll
-    for (int p = 0; p < 8; ++p) sts128(wr + ((p ^ (lane & 7)) << 4), make_float4(v[4 * p], v[4 * p + 1], v[4 * p + 2], v[4 * p + 3]));
-    __syncwarp();
-#ifdef LLB_GEMM_TRACE
-    const long long k2 = clock64();
-    float sink = res[0].x + res[7].w;   // forces the residual loads to have landed
-    asm volatile("" ::"f"(sink));
-    const long long k3 = clock64();
-#endif
-    // coalesced layout (8 lanes per 128-byte row segment): add the residual, write x back in place, pack xb
-    const float* xp = a.xrow + c;
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int rr = it * 4 + rsub;
-      const uint32_t xa = a.xstg + rr * 128 + ((sl ^ (rr & 7)) << 4);
-      const float4 d = lds128(xa);
-      const float4 o = make_float4(res[it].x + d.x, res[it].y + d.y, res[it].z + d.z, res[it].w + d.w);
-      if (GLN_EXP(64)) {
-        if (it * 4 < a.rows_left) *reinterpret_cast<float4*>(const_cast<float*>(xp)) = o;   // experiment: x through generic stores
-      } else {
-        sts128(xa, o);
-      }
-      sts64(a.xbstg + rr * 64 + ((((sl >> 1) ^ (rr >> 1)) & 3) << 4) + (sl & 1) * 8, pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
-      // next chunk's residual segment: in flight during that chunk's TMEM load and arithmetic
-      if (c + 32 < GLN_BN / 2 && it * 4 < a.rows_left && !GLN_EXP(4)) res[it] = *reinterpret_cast<const float4*>(xp + 32);
-      xp += a.xstride;
-    }
-    fence_proxy_async_smem();
-    __syncwarp();
-    if (elect_one()) {
-      if (!GLN_EXP(1) && !GLN_EXP(64)) tma_store_2d(tmX, reinterpret_cast<const void*>(__cvta_shared_to_generic(a.xstg)), a.gcol + c, a.grow);
-      if (!GLN_EXP(2)) tma_store_2d(tmXb, reinterpret_cast<const void*>(__cvta_shared_to_generic(a.xbstg)), a.gcol + c, a.grow);
-      bulk_commit();
-    }
-#ifdef LLB_GEMM_TRACE
-    const long long k4 = clock64();
-    tt0 += k1 - k0, tt1 += k2 - k1, tt2 += k3 - k2, tt3 += k4 - k3;
-#endif
-  }
-#ifdef LLB_GEMM_TRACE
-  if (a.trace_tile >= 0) {
-    GLN_TRACE(a.trace_tile, 11, tt0);
-    GLN_TRACE(a.trace_tile, 12, tt1);
-    GLN_TRACE(a.trace_tile, 13, tt2);
-    GLN_TRACE(a.trace_tile, 14, tt3);
-  }
-#endif
-}
 
 // Pass 2 with the residual travelling through TMA in BOTH directions (CTA-pair kernel): the residual box of a chunk is
 // TMA-loaded into the warp's swizzled staging tile, each thread (= TMEM lane = row) adds its 32 normalised, modulated
@@ -494,255 +364,6 @@ __device__ __forceinline__ float2 gln_pass1(uint32_t t_row, uint32_t bias_s) {
   }
   return make_float2(s, ss);
 }
-
-// Warp roles: 0..7 epilogue, 8 TMA producer, 9 MMA issuer, 10 TMEM allocator, 11 modulation stager.
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                       const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXb,
-                       const __grid_constant__ CUtensorMap tmXpf, int M, int K, int CL,
-                       GemmLnArgs e) {
-  using S = GlnSmem;
-  constexpr int STAGES = GLN_STAGES;
-  constexpr int BN = GLN_BN;
-  extern __shared__ uint8_t smem_raw[];
-  // keep every pointer a shared-space offset from smem_raw (a cast through uintptr_t would turn the accesses generic)
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* smA = smem;
-  uint8_t* smB = smem + STAGES * S::A_BYTES;
-  float* modS = reinterpret_cast<float*>(smem + S::OFF_MOD);
-  float* biasS = reinterpret_cast<float*>(smem + S::OFF_BIAS);
-  float2* statsS = reinterpret_cast<float2*>(smem + S::OFF_STATS);
-  float2* sendS = reinterpret_cast<float2*>(smem + S::OFF_SEND);
-  float2* partS = reinterpret_cast<float2*>(smem + S::OFF_PART);
-  int2* rowinfoS = reinterpret_cast<int2*>(smem + S::OFF_ROWINFO);
-  int* glistS = reinterpret_cast<int*>(smem + S::OFF_GLIST);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BARS);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + STAGES;
-  uint64_t* tmem_full = bars + 2 * STAGES;
-  uint64_t* tmem_empty = bars + 2 * STAGES + 2;
-  uint64_t* stats_full = bars + 2 * STAGES + 4;
-  uint64_t* mod_full = bars + 2 * STAGES + 6;
-  uint64_t* mod_empty = bars + 2 * STAGES + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 10);
-
-  const int warp = uniform_warp_idx();
-  const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_rank();
-  const int cluster_id = blockIdx.x / CL, num_clusters = gridDim.x / CL;
-  const int num_m = (M + GEMM_BM - 1) / GEMM_BM;
-  const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
-  const int n0 = (int)rank * BN;
-  const int N = CL * BN;
-
-  if (warp == GEMM_EPI_WARPS && elect_one()) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
-    tma_prefetch_desc(&tmX);
-    tma_prefetch_desc(&tmXb);
-    tma_prefetch_desc(&tmXpf);
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], GEMM_EPI_WARPS);
-      mbar_init(&stats_full[a], 1);
-      mbar_init(&mod_full[a], 1);
-      mbar_init(&mod_empty[a], GEMM_EPI_WARPS);
-    }
-    fence_mbar_init();
-  }
-  if (warp == GEMM_EPI_WARPS + 2) tmem_alloc(tmem_slot, 2 * BN);
-  if (threadIdx.x < BN) biasS[threadIdx.x] = e.bias ? e.bias[n0 + threadIdx.x] : 0.0f;
-  tc_fence_before();
-  __syncthreads();
-  cluster_barrier();   // every CTA's barriers are initialised before anyone signals them remotely
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == GEMM_EPI_WARPS) {
-    // ---------------- TMA producer (converged warp, one elected lane issues) ----------------
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int mt = cluster_id; mt < num_m; mt += num_clusters) {
-      const int m0 = mt * GEMM_BM;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&empty[stage], phase ^ 1);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&full[stage], S::STAGE_BYTES);
-          tma_load_2d(smA + stage * S::A_BYTES, &tmA, &full[stage], kb * GEMM_BK, m0);
-          tma_load_2d(smB + stage * S::B_BYTES, &tmB, &full[stage], kb * GEMM_BK, n0);
-        }
-        __syncwarp();
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1;
-        }
-      }
-    }
-  } else if (warp == GEMM_EPI_WARPS + 1) {
-    // ---------------- MMA issuer (converged warp, one elected lane issues; operands in uniform registers) ----------------
-    constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
-    const uint64_t a_desc0 = umma_desc_k128(smem_u32(smA));
-    const uint64_t b_desc0 = umma_desc_k128(smem_u32(smB));
-    int stage = 0;
-    uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    int tcount = 0;
-    for (int mt = cluster_id; mt < num_m; mt += num_clusters, ++tcount) {
-      if (lane == 0) GLN_TRACE(tcount, 8, clock64());
-      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-      if (lane == 0) GLN_TRACE(tcount, 9, clock64());
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BN;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&full[stage], phase);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint64_t a_desc = a_desc0 + (uint64_t)(stage * (S::A_BYTES >> 4));
-          const uint64_t b_desc = b_desc0 + (uint64_t)(stage * (S::B_BYTES >> 4));
-#pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(&empty[stage]);
-        }
-        __syncwarp();
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1;
-        }
-      }
-      if (elect_one()) umma_commit(&tmem_full[acc]);
-      __syncwarp();
-      if (lane == 0) GLN_TRACE(tcount, 10, clock64());
-      if (++acc == 2) {
-        acc = 0;
-        acc_phase ^= 1;
-      }
-    }
-  } else if (warp == GEMM_EPI_WARPS + 3) {
-    // ---------------- modulation stager (runs up to two tiles ahead of the epilogue) ----------------
-    // Per tile: which modulation rows do its 128 token rows use (runs of equal row_group), stage gate*(1+scale) and
-    // gate*shift of those rows in shared memory, and pull the tile's residual rows into L2 for the epilogue's pass 2.
-    int st = 0;
-    uint32_t ph = 0;
-    for (int mt = cluster_id; mt < num_m; mt += num_clusters) {
-      const int m0 = mt * GEMM_BM;
-      mbar_wait(&mod_empty[st], ph ^ 1);
-      gln_stage_tile(e, &tmXpf, modS + (size_t)st * S::MOD_STAGE_FLOATS, rowinfoS + st * GEMM_BM, glistS + st * 8, m0, n0, M, lane);
-      if (lane == 0) mbar_arrive(&mod_full[st]);
-      if (++st == 2) {
-        st = 0;
-        ph ^= 1;
-      }
-    }
-  } else if (warp < GEMM_EPI_WARPS) {
-    // ---------------- epilogue: LayerNorm over the cluster's full row, modulate, gate, residual ----------------
-    const int q = warp & 3, ch = warp >> 2;          // TMEM lane quarter, column half
-    const int rloc = q * 32 + lane;                  // this thread's row inside the tile (thread == TMEM lane)
-    const int cbase = ch * (BN / 2);                 // first of this warp's 128 columns (CTA-local)
-    const float inv_n = 1.0f / (float)N;
-    const int sl = lane & 7, rsub = lane >> 3;       // coalesced phase: 16-byte slot / row within a group of 4 rows
-    GlnPass2 a;
-    a.xstg = smem_u32(smem + S::OFF_XSTG + warp * S::XSTG_PER_WARP);
-    a.xbstg = smem_u32(smem + S::OFF_XBSTG + warp * S::XBSTG_PER_WARP);
-    a.bias_s = smem_u32(biasS + cbase);
-    a.xstride = (size_t)4 * e.ldx;
-    a.gcol = n0 + cbase;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    int tcount = 0;
-    const bool tr = warp == 0 && lane == 0;
-    for (int mt = cluster_id; mt < num_m; mt += num_clusters, ++tcount) {
-      const int m0 = mt * GEMM_BM;
-      if (tr) GLN_TRACE(tcount, 0, clock64());
-      // this tile's statistics: CL CTAs x 128 rows x one float2 will be deposited in statsS[acc]
-      if (warp == 0 && lane == 0) mbar_arrive_expect_tx(&stats_full[acc], (uint32_t)(CL * GEMM_BM * 8));
-      // ---- (A) the tile's modulation rows are staged (normally long before the accumulators are ready)
-      mbar_wait(&mod_full[acc], acc_phase);
-      const int2 info = rowinfoS[acc * GEMM_BM + rloc];
-      const bool staged = glistS[acc * 8 + 4] <= GLN_MAX_GROUPS;
-      // ---- (B) accumulators ready: pass 1, row statistics over this warp's 128 columns
-      if (tr) GLN_TRACE(tcount, 1, clock64());
-      mbar_wait(&tmem_full[acc], acc_phase);
-      if (tr) GLN_TRACE(tcount, 2, clock64());
-      tc_fence_after();
-      a.t_row = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16) + cbase;
-      partS[ch * GEMM_BM + rloc] = gln_pass1(a.t_row, a.bias_s);
-      epi_bar_sync();
-      if (ch == 0) {
-        // combine the two column halves; each of warps 0..3 ships its 32 rows (256 bytes) to every CTA of the cluster
-        const float2 p0 = partS[rloc], p1 = partS[GEMM_BM + rloc];
-        float2* mine = sendS + (size_t)acc * GEMM_BM + q * 32;
-        mine[lane] = make_float2(p0.x + p1.x, p0.y + p1.y);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          const uint32_t src = smem_u32(mine);
-          const uint32_t dst = smem_u32(statsS + (size_t)(acc * GLN_MAX_CL + rank) * GEMM_BM + q * 32);
-          const uint32_t bar = smem_u32(&stats_full[acc]);
-          for (int d = 0; d < CL; ++d) dsmem_bulk_copy(map_to_cta(dst, d), src, 256, map_to_cta(bar, d));
-        }
-      }
-      if (tr) GLN_TRACE(tcount, 3, clock64());
-      // first residual chunk: in flight while the statistics travel
-      const int row0 = m0 + q * 32 + rsub;   // this lane's first row of the coalesced phase
-      a.rows_left = M - row0;
-      a.grow = m0 + q * 32;
-      a.xrow = e.x + (size_t)row0 * e.ldx + n0 + cbase + sl * 4;
-      float4 res[8];
-#pragma unroll
-      for (int it = 0; it < 8; ++it)
-        res[it] = (it * 4 < a.rows_left) ? *reinterpret_cast<const float4*>(a.xrow + it * a.xstride) : make_float4(0.f, 0.f, 0.f, 0.f);
-      // ---- (C) the whole row's statistics have arrived from every CTA of the cluster
-      mbar_wait(&stats_full[acc], acc_phase);
-      if (tr) GLN_TRACE(tcount, 4, clock64());
-      {
-        float s = 0.f, ss = 0.f;
-        const float2* base = statsS + (size_t)acc * GLN_MAX_CL * GEMM_BM;
-        for (int src = 0; src < CL; ++src) {
-          const float2 p = base[src * GEMM_BM + rloc];
-          s += p.x, ss += p.y;
-        }
-        const float mean = s * inv_n;
-        const float var = fmaxf(ss * inv_n - mean * mean, 0.0f);
-        a.rstd = rsqrtf(var + 1e-5f);
-        a.nmr = -mean * a.rstd;
-      }
-      a.trace_tile = tr ? tcount : -1;
-      if (staged) {
-        a.mod_s = smem_u32(modS + (size_t)acc * S::MOD_STAGE_FLOATS + (size_t)info.x * 2 * BN + cbase);
-        gln_pass2<true>(a, &tmX, &tmXb, res, lane);
-      } else {
-        const size_t off = (size_t)info.y * e.mod_ld + n0 + cbase;
-        a.g_shift = e.shift + off, a.g_scale = e.scale + off, a.g_gate = e.gate + off;
-        gln_pass2<false>(a, &tmX, &tmXb, res, lane);
-      }
-      if (tr) GLN_TRACE(tcount, 5, clock64());
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&tmem_empty[acc]);
-        mbar_arrive(&mod_empty[acc]);
-      }
-      if (++acc == 2) {
-        acc = 0;
-        acc_phase ^= 1;
-      }
-    }
-    if (lane == 0) bulk_wait_all();
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_barrier();   // nobody exits while a peer may still push statistics into its shared memory
-  if (warp == GEMM_EPI_WARPS + 2) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BN);
-  }
-}
-
 
 // ------------------------------------------------------------------------------------------------------------------
 // N = 1024 variant on the CTA-pair (cta_group::2) main loop.
@@ -1130,69 +751,14 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
 }  // namespace
 
-int gemm_ln_mode() {
+bool gemm_ln_enabled() {
   static int mode = -1;
   if (mode < 0) {
     const char* v = getenv("LLB_FUSED_LN");
-    mode = (v && v[0] >= '0' && v[0] <= '4') ? v[0] - '0' : 3;
+    mode = (v && v[0] == '0') ? 0 : 1;
   }
-  return mode;
+  return mode != 0;
 }
-
-int launch_gemm_ln(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const GemmLnArgs& e, cudaStream_t stream,
-                   GemmCounters* ctr) {
-  if (M <= 0) return LLB_OK;
-  LLB_CHECK_ARG(gemm_ln_supported(N, K), "gemm_ln: N=%d must be 256, 512, 768 or 1024 and K=%d a multiple of 8", N, K);
-  LLB_CHECK_ARG(lda % 8 == 0 && ldw % 8 == 0 && e.ldx % 4 == 0 && e.ldxb % 8 == 0 && e.mod_ld % 4 == 0,
-                "gemm_ln: leading dimensions must keep rows 16-byte aligned (lda=%d ldw=%d ldx=%d ldxb=%d mod_ld=%d)", lda, ldw, e.ldx,
-                e.ldxb, e.mod_ld);
-  LLB_CHECK_ARG(e.row_group && e.shift && e.scale && e.gate && e.x && e.xb, "gemm_ln: null operand");
-  LLB_CHECK_ARG(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(e.x) |
-                  reinterpret_cast<uintptr_t>(e.shift) | reinterpret_cast<uintptr_t>(e.scale) | reinterpret_cast<uintptr_t>(e.gate)) & 15) == 0 &&
-                    (reinterpret_cast<uintptr_t>(e.xb) & 15) == 0 && (e.bias == nullptr || (reinterpret_cast<uintptr_t>(e.bias) & 3) == 0),
-                "gemm_ln: operands must be 16-byte aligned");
-  LLB_CHECK_ARG(A != (const void*)e.xb, "gemm_ln: the A operand must not alias the bf16 output");
-  const int CL = N / GLN_BN;
-  CUtensorMap tmA, tmB;
-  LLB_TRY(make_tensor_map_2d(&tmA, A, 2, M, K, lda, GEMM_BK, GEMM_BM, 128));
-  LLB_TRY(make_tensor_map_2d(&tmB, W, 2, N, K, ldw, GEMM_BK, GLN_BN, 128));
-  CUtensorMap tmX, tmXb;
-  LLB_TRY(make_tensor_map_2d(&tmX, e.x, 4, M, N, e.ldx, 32, 32, 128));
-  LLB_TRY(make_tensor_map_2d(&tmXb, e.xb, 2, M, N, e.ldxb, 32, 32, 64));
-  CUtensorMap tmXpf;   // L2-prefetch view of x: one box = one CTA's block of a tile
-  LLB_TRY(make_tensor_map_2d(&tmXpf, e.x, 4, M, N, e.ldx, GLN_BN, GEMM_BM, 0));
-  static bool configured = false;
-  static int max_clusters[GLN_MAX_CL + 1] = {0, 0, 0, 0, 0};
-  if (!configured) {
-    LLB_CUDA_OK(cudaFuncSetAttribute(gemm_ln_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GlnSmem::TOTAL));
-    configured = true;
-  }
-  cudaLaunchConfig_t cfg = {};
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-  cfg.blockDim = dim3(GEMM_THREADS), cfg.dynamicSmemBytes = GlnSmem::TOTAL, cfg.stream = stream, cfg.attrs = attr, cfg.numAttrs = 1;
-  if (max_clusters[CL] == 0) {
-    // persistent grid: as many clusters as the device can hold at once (GPC boundaries can strand a few SMs at CL = 4)
-    cfg.gridDim = dim3(CL * (num_sms() / CL));
-    int n = 0;
-    LLB_CUDA_OK(cudaOccupancyMaxActiveClusters(&n, gemm_ln_cluster_kernel, &cfg));
-    LLB_CHECK_ARG(n > 0, "gemm_ln: a cluster of %d CTAs does not fit on this device", CL);
-    max_clusters[CL] = n;
-  }
-  const int num_m = ceil_div(M, GEMM_BM);
-  const int clusters = num_m < max_clusters[CL] ? num_m : max_clusters[CL];
-  cfg.gridDim = dim3(CL * clusters);
-  {
-    ProfScope prof(ctr ? ctr->slot : LLB_PROF_GEMM_OTHER, stream);
-    LLB_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_ln_cluster_kernel, tmA, tmB, tmX, tmXb, tmXpf, M, K, CL, e));
-    note_kernel(LLB_KERN_GEMM_LN_CLUSTER);
-  }
-  LLB_CUDA_OK(cudaGetLastError());
-  if (ctr) ctr->launches++;
-  return LLB_OK;
-}
-
 
 size_t gemm_ln_pair_workspace_bytes() {
   // statistics mailboxes: [group][2 tile parities][2 ranks][4 slices][128 rows] x 16 bytes
@@ -1285,10 +851,10 @@ static int launch_gin_tail_ns(const void* A, int lda, const void* W, int ldw, in
   LLB_TRY(make_tensor_map_2d(&tmX, t.x, 4, M, N, t.ldx, 32, 32, 128));
   LLB_TRY(make_tensor_map_2d(&tmXb, t.xb, 2, M, N, t.ldxb, 32, 32, 64));
   LLB_TRY(make_tensor_map_2d(&tmXpf, t.x, 4, M, N, t.ldx, GLN_BN, GEMM_BM, 0));
-  // (5 stages, one staging tile) or (4 stages, two staging tiles: the next chunk's residual is loaded a chunk ahead)
-  static const int cfg_env = getenv("LLB_GIN_TAIL_CFG") ? atoi(getenv("LLB_GIN_TAIL_CFG")) : -1;
-  const bool long_k = cfg_env >= 0 ? (cfg_env & 1) == 0 : K > 2048;
-  const int prefetch_x = (cfg_env >= 0 ? (cfg_env >> 1) & 1 : 0) | (t.a_f16 ? 2 : 0);
+  // long K: (5 stages, one staging tile); short K: (4 stages, two staging tiles, the next chunk's residual loaded a chunk ahead).
+  // Measured at K = 3072 (ncu, tensor pipe active): 67 % vs 60 %, and an L2 prefetch of the next tile's residual block loses too.
+  const bool long_k = K > 2048;
+  const int prefetch_x = t.a_f16 ? 2 : 0;
   auto kern = long_k ? gemm_ln_pair_kernel<5, 1, 1, NS, true> : gemm_ln_pair_kernel<4, 1, 2, NS, true>;
   const int smem_bytes = long_k ? GlnPairSmemT<5, 1, 1>::TOTAL : GlnPairSmemT<4, 1, 2>::TOTAL;
   static bool configured[2] = {false, false};
@@ -1366,15 +932,6 @@ int launch_gin_tail(const void* A, int lda, const void* W, int ldw, int M, int N
 extern "C" void llb_gln_set_trace(long long* p) { cudaMemcpyToSymbol(llb::g_gln_trace, &p, sizeof(p)); }
 extern "C" void llb_gln_set_exp(int m) { cudaMemcpyToSymbol(llb::g_gln_exp, &m, sizeof(m)); }
 #endif
-
-extern "C" int llb_gemm_ln_residual(const void* A, int lda, const void* W, int ldw, const float* bias, const int32_t* row_group,
-                                    const float* shift, const float* scale, const float* gate, int mod_ld, float* x, int ldx,
-                                    void* xb, int ldxb, int M, int N, int K, llb_stream_t stream) {
-  LLB_TRY(llb::require_sm100());
-  LLB_CHECK_ARG(A && W, "llb_gemm_ln_residual: null operand");
-  llb::GemmLnArgs e{bias, row_group, shift, scale, gate, mod_ld, x, ldx, reinterpret_cast<__nv_bfloat16*>(xb), ldxb};
-  return llb::launch_gemm_ln(A, lda, W, ldw, M, N, K, e, (cudaStream_t)stream, nullptr);
-}
 
 extern "C" int llb_gemm_ln_workspace_bytes(size_t* bytes) {
   LLB_CHECK_ARG(bytes, "llb_gemm_ln_workspace_bytes: null argument");

@@ -6,28 +6,21 @@
 // kernel between two GEMMs.  Here the LayerNorm runs on the fp32 accumulators in TMEM: 10 bytes per element, all of
 // it overlapped with the next tile's MMAs.
 //
-// A full output row (N = H columns) has to be visible to normalise it, so a CLUSTER of CL = N / 256 CTAs owns one
-// 128-row tile: CTA r computes columns [256 r, 256 r + 256) with the same pipeline as gemm_tcgen05_kernel<256>
-// (TMA producer warp, single-thread tcgen05.mma issuer, 2 TMEM accumulator stages, 8 epilogue warps).  The epilogue
-//   pass 1  tcgen05.ld -> per-row sum / sum of squares over the CTA's 256 columns; every CTA pushes its partials into
-//           all CTAs of the cluster through distributed shared memory (st.shared::cluster) and arrives on their
-//           mbarrier (release.cluster); nobody waits on a cluster-wide barrier, so the producer / MMA warps of the
-//           four SMs keep streaming.
+// A full output row (N = H columns) has to be visible to normalise it, and 1024 fp32 accumulator columns are twice one SM's
+// tensor memory, so a row is shared: FOUR independent CTA pairs (cta_group::2) form a group that owns a 256-row block, CTA
+// (slice s, rank r) holds rows [128 r, +128) x columns [256 s, +256).  The epilogue
+//   pass 1  tcgen05.ld -> per-row sum / sum of squares over the CTA's 256 columns; the four CTAs of equal rank exchange them
+//           through mailboxes in L2 (data and tag in the same atomic 8-byte halves: no fence, no counter);
 //   pass 2  tcgen05.ld again (TMEM reads are cheap) -> normalise, modulate with the tile's (<= 4) modulation rows staged
-//           in shared memory, gate -> transpose through a swizzled per-warp staging tile -> coalesced 128-byte
-//           row segments: residual read (prefetched before the TMEM load), x store, bf16 xb store.
+//           in shared memory, gate -> residual chunk in and result out through TMA, in the thread = row layout.
+// (A 4-CTA-cluster variant with the statistics in distributed shared memory existed in round 1; it lost to this kernel at every
+// shape the sampler uses and was removed.)
 #pragma once
 #include "llb_gemm.cuh"
 
 namespace llb {
 
 constexpr int GLN_BN = 256;
-#ifndef GLN_STAGES_OVERRIDE
-constexpr int GLN_STAGES = 3;
-#else
-constexpr int GLN_STAGES = GLN_STAGES_OVERRIDE;
-#endif
-constexpr int GLN_MAX_CL = 4;
 constexpr int GLN_PAIR_MAX_GROUPS = 18;   // 4-pair groups of the CTA-pair variant (72 of the B200's 74 pairs)
 constexpr int GLN_MAX_GROUPS = 4;   // modulation rows staged per tile (a 128-row tile of 50-atom molecules touches <= 4)
 
@@ -44,12 +37,10 @@ struct GemmLnArgs {
   int ldxb;
 };
 
-// N must be CL * 256 with CL in 1..4 (hidden sizes 256 / 512 / 768 / 1024); callers fall back to GEMM + row kernel otherwise.
-inline bool gemm_ln_supported(int N, int K) { return N % GLN_BN == 0 && N / GLN_BN >= 1 && N / GLN_BN <= GLN_MAX_CL && K % 8 == 0; }
-int gemm_ln_mode();       // env LLB_FUSED_LN, 0..3 (default 3): see dit_forward
-inline bool gemm_ln_enabled() { return gemm_ln_mode() != 0; }
-int launch_gemm_ln(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const GemmLnArgs& e, cudaStream_t stream,
-                   GemmCounters* ctr);
+// Fused GEMM + LayerNorm tails exist for N = 1024 (four CTA pairs per 256-row block, GraphDiT) and N = 768 (three, GIN):
+// a full output row has to fit the pairs' tensor memory.  Other widths use GEMM + row kernel.
+inline bool gemm_ln_supported(int N, int K) { return N == 4 * GLN_BN && K % 8 == 0; }
+bool gemm_ln_enabled();   // LLB_FUSED_LN=0 selects GEMM + row kernel for the GraphDiT block tails (A-B comparison, pinned multi-GPU tests)
 
 // Tail of a GIN layer fused into the second linear of the node MLP (graph_encoder/model.py:131-149, graph_predictor/model.py:318-348):
 //   h[r,:] = gate_g * act( LN(A[r,:] . W^T + bias) * s1 + sh ) + h[r,:] + addvec_g      g = row_group[r] (graph of node r)

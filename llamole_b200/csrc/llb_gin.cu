@@ -761,8 +761,7 @@ static void launch_softmax_topk(const float* logits, int rows, int W, int ld, in
   const bool vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0);
   const long long r_need = ((long long)7 * k * 4096 + W - 1) / W;
   const int R = r_need < 4 ? 4 : (int)r_need;
-  static const bool no_thresh = getenv("LLB_TOPK_THRESH") && getenv("LLB_TOPK_THRESH")[0] == '0';
-  if (vec && W >= 16384 && R <= 32 && !no_thresh) {
+  if (vec && W >= 16384 && R <= 32) {
     gin_topk_thresh_kernel<<<rows, 1024, 0, s>>>(logits, ld, W, k, R, topv, topi, flags);
     gin_topk_stream_kernel<<<rows, 1024, 0, s>>>(logits, ld, W, k, topv, topi, flags, 1);
   } else {

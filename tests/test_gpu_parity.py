@@ -51,13 +51,14 @@ def test_gemm_matches_torch(M, N, K, act, out_f32):
 
 
 # ------------------------------------------------------------------------------------------------ fused GEMM + LN tail
-@pytest.mark.parametrize("M,N,K,group_len", [(1, 256, 64, 50), (300, 1024, 1024, 50), (1000, 1024, 4096, 50), (777, 512, 256, 7),
-                                             (4097, 1024, 1024, 50), (260, 768, 768, 3), (128 * 41 + 5, 1024, 512, 50), (256 * 40 + 130, 1024, 1024, 50),
-                                             (600, 1024, 256, 5), (2500, 1024, 4096, 13)])
-@pytest.mark.parametrize("variant", ["cluster", "pair"])
-def test_gemm_ln_residual_matches_torch(M, N, K, group_len, variant):
-    """x += gate * (LN(A W^T + b) (1 + scale) + shift) against fp32 torch; rows map to modulation rows in runs of
-    `group_len` (3 and 7 force the more-than-4-groups-per-tile path), the last run is a shared 'unconditional' row."""
+@pytest.mark.parametrize("M,N,K,group_len", [(300, 1024, 1024, 50), (1000, 1024, 4096, 50), (4097, 1024, 1024, 50), (128 * 41 + 5, 1024, 512, 50),
+                                             (256 * 40 + 130, 1024, 1024, 50), (600, 1024, 256, 5), (2500, 1024, 4096, 13), (1, 1024, 64, 50),
+                                             (777, 1024, 256, 7), (260, 1024, 768, 3)])
+def test_gemm_ln_residual_matches_torch(M, N, K, group_len):
+    """x += gate * (LN(A W^T + b) (1 + scale) + shift) against fp64 torch; rows map to modulation rows in runs of
+    `group_len` (3, 5 and 7 force the more-than-4-groups-per-tile path), the last run is a shared 'unconditional' row."""
+    import ctypes
+
     g = torch.Generator(device="cpu").manual_seed(M + N + K)
     A = (torch.randn(M, K, generator=g) * 0.5).to(DEV).bfloat16()
     W = (torch.randn(N, K, generator=g) * (1.0 / math.sqrt(K))).to(DEV).bfloat16()
@@ -72,23 +73,17 @@ def test_gemm_ln_residual_matches_torch(M, N, K, group_len, variant):
     x = x0.clone()
     xb = torch.full((M, N), float("nan"), device=DEV, dtype=torch.bfloat16)
     lib = _cabi.lib()
-    if variant == "pair":
-        if N != 1024:
-            pytest.skip("the CTA-pair variant is N = 1024 only")
-        import ctypes
-        nbytes = ctypes.c_size_t()
-        _cabi.check(lib.llb_gemm_ln_workspace_bytes(ctypes.byref(nbytes)))
-        ws = torch.full((nbytes.value,), 0x5A, device=DEV, dtype=torch.uint8)     # garbage: the launch clears what it needs
-        for _ in range(2):                                                        # twice on the same workspace
-            x.copy_(x0)
-            _cabi.check(lib.llb_gemm_ln_residual_ws(_cabi.ptr(A), K, _cabi.ptr(W), K, _cabi.ptr(bias), _cabi.ptr(groups), _cabi.ptr(shift),
-                                                    _cabi.ptr(scale), _cabi.ptr(gate), mod.shape[1], _cabi.ptr(x), N, _cabi.ptr(xb), N, M, N, K,
-                                                    _cabi.ptr(ws), nbytes.value, _cabi.stream_ptr()), "llb_gemm_ln_residual_ws")
-    else:
-        _cabi.check(lib.llb_gemm_ln_residual(_cabi.ptr(A), K, _cabi.ptr(W), K, _cabi.ptr(bias), _cabi.ptr(groups), _cabi.ptr(shift),
-                                             _cabi.ptr(scale), _cabi.ptr(gate), mod.shape[1], _cabi.ptr(x), N, _cabi.ptr(xb), N, M, N, K,
-                                             _cabi.stream_ptr()), "llb_gemm_ln_residual")
+    nbytes = ctypes.c_size_t()
+    _cabi.check(lib.llb_gemm_ln_workspace_bytes(ctypes.byref(nbytes)))
+    ws = torch.full((nbytes.value,), 0x5A, device=DEV, dtype=torch.uint8)     # garbage: the launch clears what it needs
+    before = _cabi.kernel_launches(_cabi.KERN_GEMM_LN_PAIR)
+    for _ in range(2):                                                        # twice on the same workspace
+        x.copy_(x0)
+        _cabi.check(lib.llb_gemm_ln_residual_ws(_cabi.ptr(A), K, _cabi.ptr(W), K, _cabi.ptr(bias), _cabi.ptr(groups), _cabi.ptr(shift),
+                                                _cabi.ptr(scale), _cabi.ptr(gate), mod.shape[1], _cabi.ptr(x), N, _cabi.ptr(xb), N, M, N, K,
+                                                _cabi.ptr(ws), nbytes.value, _cabi.stream_ptr()), "llb_gemm_ln_residual_ws")
     torch.cuda.synchronize()
+    assert _cabi.kernel_launches(_cabi.KERN_GEMM_LN_PAIR) == before + 2
     y = (A.double() @ W.double().t() + bias.double())
     ln = torch.nn.functional.layer_norm(y, (N,), eps=1e-5)
     gi = groups.long()
@@ -100,11 +95,16 @@ def test_gemm_ln_residual_matches_torch(M, N, K, group_len, variant):
 
 
 def test_gemm_ln_residual_rejects_unsupported_width():
+    import ctypes
+
     z = torch.zeros(8, 320, device=DEV)
     lib = _cabi.lib()
-    st = lib.llb_gemm_ln_residual(_cabi.ptr(z.bfloat16()), 320, _cabi.ptr(z.bfloat16()), 320, None, _cabi.ptr(z.int()), _cabi.ptr(z),
-                                  _cabi.ptr(z), _cabi.ptr(z), 320, _cabi.ptr(z), 320, _cabi.ptr(z.bfloat16()), 320, 8, 320, 320,
-                                  _cabi.stream_ptr())
+    nbytes = ctypes.c_size_t()
+    _cabi.check(lib.llb_gemm_ln_workspace_bytes(ctypes.byref(nbytes)))
+    ws = torch.zeros(nbytes.value, device=DEV, dtype=torch.uint8)
+    st = lib.llb_gemm_ln_residual_ws(_cabi.ptr(z.bfloat16()), 320, _cabi.ptr(z.bfloat16()), 320, None, _cabi.ptr(z.int()), _cabi.ptr(z),
+                                     _cabi.ptr(z), _cabi.ptr(z), 320, _cabi.ptr(z), 320, _cabi.ptr(z.bfloat16()), 320, 8, 320, 320,
+                                     _cabi.ptr(ws), nbytes.value, _cabi.stream_ptr())
     assert st != 0 and b"gemm_ln" in lib.llb_last_error()
 
 
@@ -464,18 +464,27 @@ def test_condition_queue_matches_direct_sampling(dit, dit_small):
     assert bool((X[valid] >= 0).all()) and bool((X[~valid] == -1).all())
 
 
-def test_dit_parity_with_fused_block_tails_forced():
-    """Below 2048 token rows the sampler picks the unfused block tails (latency regime), which is what the small fixtures
-    above exercise; the throughput path (GEMM + LayerNorm fused, LLB_FUSED_LN=3) must meet the same tolerances on the
-    same fixtures, so the denoiser tests are repeated in a child process with the fused tails forced."""
+@pytest.mark.parametrize("env,select,path", [
+    ({"LLB_ATTN": "2"}, "denoiser_logits or full_size or teacher_forced or end_to_end or degenerate", "test_gpu_parity.py"),
+    ({"LLB_ATTN": "2"}, "dit_wide", "test_gpu_parity_large.py"),
+    ({"LLB_FUSED_LN": "0"}, "dit_wide", "test_gpu_parity_large.py"),
+    ({"LLB_GIN_FUSED_TAIL": "0"}, "gin_encoder_baseline_shape or gin_predictor_baseline_shape", "test_gpu_parity_large.py"),
+])
+def test_kernel_variants_meet_the_same_tolerances(env, select, path):
+    """Every kernel variant that an environment switch can select is held to the default path's tolerances: the tcgen05
+    attention kernel (LLB_ATTN=2: P in tensor memory), the unfused GraphDiT block tails at a size where the fused ones are
+    the default (LLB_FUSED_LN=0), the GIN node MLP with a separate layer-tail row kernel (LLB_GIN_FUSED_TAIL=0).  The switches are
+    read once per process, hence the child process."""
     import subprocess
     import sys
 
-    if os.environ.get("LLB_FUSED_LN"):
-        pytest.skip("already running with LLB_FUSED_LN set")
-    env = dict(os.environ, LLB_FUSED_LN="3")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k",
-                        "denoiser_logits or full_size or teacher_forced or end_to_end"], env=env, capture_output=True, text=True, timeout=900)
+    if any(os.environ.get(k) for k in env):
+        pytest.skip("already running with the switch set")
+    child = dict(os.environ, **env)
+    child.pop("LLB_PARITY_OUT", None)
+    child["LLB_PARITY_OUT"] = os.devnull
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(os.path.dirname(os.path.abspath(__file__)), path), "-q", "-x", "-m", "gpu",
+                        "-k", select], env=child, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert " passed" in r.stdout and "failed" not in r.stdout
 

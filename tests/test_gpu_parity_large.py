@@ -142,7 +142,8 @@ def test_dit_wide_batch_vs_oracle(dit_wide):
         qX, qE = ex(B, N, 16), ex(B, N, N, 5)
         Xn, En, _, _, pX, pE = O.reverse_step(sd, cfg, tb, U, sched, X, E, node_mask, y, txt, t, qX, qE, return_probs=True)
     assert _cabi.kernel_launches(_cabi.KERN_GEMM_2CTA) > k2, "qkv / fc1 must have run on the CTA-pair GEMM"
-    assert _cabi.kernel_launches(_cabi.KERN_GEMM_LN_PAIR) > kp, "the block tails must have run on the fused GEMM + LayerNorm pair kernel"
+    if os.environ.get("LLB_FUSED_LN") != "0":
+        assert _cabi.kernel_launches(_cabi.KERN_GEMM_LN_PAIR) > kp, "the block tails must have run on the fused GEMM + LayerNorm pair kernel"
     print(f"\n[parity] denoiser at {2 * int(n_nodes.sum())} token rows (H=1024, depth 3) vs fp32 oracle: max|d|={worst[0]:.4f} rms={worst[1]:.5f}")
     assert worst[0] <= 0.10 and worst[1] <= 0.02, worst
     # full reverse step with the same pre-drawn noise: categories agree wherever the oracle's margin exceeds the propagated
