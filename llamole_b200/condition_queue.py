@@ -146,6 +146,15 @@ class ConditionQueue:
             self.flush()
         return self._done[ticket] if keep else self._done.pop(ticket)
 
+    def smiles(self, ticket: Ticket, backend=None, workers: Optional[int] = None) -> List[Optional[str]]:
+        """The request's molecules as SMILES (None where the conversion fails, like `GraphDiT.generate`), converted by `workers`
+        processes (`smiles_io.graphs_to_smiles_parallel`; backend = the reference's RDKit `graph_to_smiles` unless given)."""
+        from .graph_decoder import _smiles_backend
+        from .smiles_io import graphs_to_smiles_parallel
+
+        return graphs_to_smiles_parallel(self.molecules(ticket), self.model.atom_decoder, backend=backend if backend is not None else _smiles_backend(),
+                                         workers=workers)
+
     def molecules(self, ticket: Ticket) -> List[List[torch.Tensor]]:
         """The request's graphs as `[atom_types (n,), bond_types (n,n)]` pairs, the input of `graph_to_smiles`
         (diffusion_model.py:297-304)."""

@@ -145,6 +145,8 @@ class GraphDiT(nn.Module):
         self.node_prob = n_hist / n_hist.sum()
         self.betas, self.alphas_bar = cosine_schedule(self.T)
         self._engine = None
+        # worker processes of the graph -> SMILES conversion after sampling (1 = the reference's serial loop on this thread)
+        self.smiles_workers = 1
 
     # ------------------------------------------------------------------ reference surface
     def init_model(self, model_dir, verbose=False):
@@ -194,6 +196,10 @@ class GraphDiT(nn.Module):
         for i in range(Xc.shape[0]):
             n = int(nn_[i])
             molecule_list.append([Xc[i, :n], Ec[i, :n, :n]])
+        if self.smiles_workers > 1:
+            from .smiles_io import graphs_to_smiles_parallel
+
+            return graphs_to_smiles_parallel(molecule_list, self.atom_decoder, backend=_smiles_backend(), workers=self.smiles_workers)
         return _smiles_backend()(molecule_list, self.atom_decoder)
 
     # ------------------------------------------------------------------ accelerated path

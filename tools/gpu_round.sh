@@ -6,7 +6,8 @@ quick=${2:-}
 out=gpurun_out
 mkdir -p $out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > $out/gpu_$tag.txt 2>&1
-timeout 900 python -m pytest tests -m gpu -x -q > $out/pytest_gpu_$tag.log 2>&1
+rm -f $out/parity.json
+timeout 1500 python -m pytest tests -m gpu -x -q -s > $out/pytest_gpu_$tag.log 2>&1
 echo "pytest rc=$?" >> $out/pytest_gpu_$tag.log
 tail -3 $out/pytest_gpu_$tag.log
 timeout 600 python bench.py > $out/bench_$tag.json 2> $out/bench_$tag.err
@@ -21,7 +22,12 @@ if [ -z "$quick" ]; then
       python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $out/ncu_block_$tag.log 2>&1
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:dit_step -s 1 -c 1 -o $out/prof_dit_step_$tag -f \
       python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $out/ncu_step_$tag.log 2>&1
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:gin_ -s 40 -c 14 -o $out/prof_gin_$tag -f \
-      python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $out/ncu_gin_$tag.log 2>&1
+  # one GIN encoder layer set (aggregate, statistics GEMM, mlp0 with LayerNorm + GELU epilogue, fused GEMM + layer tail, pooling)
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:"gin_|gemm_ln_pair_kernel|gemm_tcgen05_2cta" -s 12 -c 24 -o $out/prof_gin_$tag -f \
+      python bench.py --only gin > $out/ncu_gin_$tag.log 2>&1
+  # the fused predictor head (pilot GEMM, head GEMM with the top-k epilogue, select kernel)
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:"EpiHeadTopk|gin_head_" -c 6 -o $out/prof_head_$tag -f \
+      python bench.py --only predictor > $out/ncu_head_$tag.log 2>&1
+  cp $out/parity.json $out/parity_$tag.json 2>/dev/null
 fi
 ls -la $out | tail -20

@@ -82,7 +82,7 @@ if os.path.exists(lpath):
         f.write(body)
 
 # ---------------------------------------------------------------- --set full reports
-for what in ("dit_block", "dit_step", "gin", "gemm", "attn", "ln"):
+for what in ("dit_block", "dit_step", "gin", "head", "gemm", "attn", "ln"):
     rep = os.path.join(G, f"prof_{what}_{tag}.ncu-rep")
     if not os.path.exists(rep):
         continue
@@ -127,6 +127,17 @@ if os.path.exists(rep):
     for name, byts in raw_rows(rep):
         if "gin_aggregate" in name:
             traffic.setdefault("gin_aggregate", []).append(byts)
+        elif "gemm_ln_pair_kernel" in name:
+            traffic.setdefault("gin_tail", []).append(byts)
+        elif "EpiLnGelu" in name:
+            traffic.setdefault("gin_mlp0", []).append(byts)
+        elif "EpiRowSq" in name:
+            traffic.setdefault("gin_stats", []).append(byts)
+rep = os.path.join(G, f"prof_head_{tag}.ncu-rep")
+if os.path.exists(rep):
+    for name, byts in raw_rows(rep):
+        if "EpiHeadTopk" in name:
+            traffic.setdefault("head_topk", []).append(byts)
 if traffic:
     with open(os.path.join(P, "traffic.json"), "w") as f:
         json.dump({"source": f"{rnd}: ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch (mean over captured launches)",
@@ -139,4 +150,7 @@ for name in (f"bench_{tag}.json", f"bench_ref_{tag}.json"):
         if b:
             with open(os.path.join(P, f"{rnd}_{name.replace('_' + tag, '')}"), "w") as f:
                 json.dump(b, f, indent=1)
+src = os.path.join(G, f"parity_{tag}.json")
+if os.path.exists(src):
+    shutil.copy(src, os.path.join(P, f"parity_{rnd}.json"))
 print("\n".join(sorted(os.listdir(P))))
