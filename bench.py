@@ -350,6 +350,16 @@ def main():
                     "frac": ach / pk["tf_sustained"], "traffic": ncu_traffic(dom), "peak_source": pk["source"] + " (sustained: timed inside a long step)",
                     "launch_ms": dur * 1e3, "flops_per_launch": gemm_flops[dom],
                     "whole_step": {"flops_per_step": flops_step, "achieved": flops_step / (ms_step / 1e3) / 1e12, "frac": step_frac}}
+    # the fused posterior + guidance + sampling kernel (K8-K10): HBM-bound by construction, a rounding error of the step.  Bytes per
+    # molecule-step as implemented: both passes' raw output rows (2 n x 268 fp32) + the modulation rows + int8 state in and out.
+    step_kernel = None
+    if "dit_step" in prof:
+        d0 = 16 + 5 * N
+        sk_bytes = float(sum(2 * int(n) * (d0 + 2) * 4 for n in n_nodes)) + B * (2 * 2 * d0 * 4 + 2 * (N + N * N))
+        sk_ms = prof["dit_step"][0] / prof["dit_step"][1]
+        step_kernel = {"bound": "hbm", "kernel": "dit_step_kernel", "bytes_per_launch": sk_bytes, "launch_ms": sk_ms, "achieved": sk_bytes / (sk_ms / 1e3) / 1e9,
+                       "peak": pk["hbm"], "unit": "GB/s", "frac": sk_bytes / (sk_ms / 1e3) / 1e9 / pk["hbm"], "share_of_step": sk_ms / ms_step,
+                       "note": "latency-bound (one CTA per molecule, two 106 KB CTAs per SM), not bandwidth-bound: 1.3 % of the step"}
     # ------------------------------------------------------------------ e2e through the public API (host buffers)
     k_e2e = min(args.steps, 10)
     outX = torch.empty((B, N), dtype=torch.int64).pin_memory()
@@ -456,7 +466,7 @@ def main():
             "comm": {"backend": "nccl" if world > 1 else None, "nranks": world, "comm_ms": comm_ms, "comm_ms_per_step": comm_ms / args.steps,
                      "what": "one all-gather of the packed sampled graphs (sharding.pack_graphs, 1327 B/molecule) + unpack, once per sampling run; "
                              "included in ms_per_step" if world > 1 else "single GPU: no exchange"},
-            "latency": latency,
+            "latency": latency, "sampling_kernel": step_kernel,
             "gpu_launches": int(dit_launches + gin.pop("_launches") + (pred.pop("_launches") if pred else 0)), "roofline": roofline,
             "cpu_baseline": cpu, "kernel_breakdown": breakdown, "ragged": ragged, "gin": gin, "predictor": pred,
         }

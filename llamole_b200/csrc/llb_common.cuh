@@ -58,6 +58,26 @@ struct ProfScope {
 
 void note_kernel(int family);   // llb_kernel_launches counters
 
+// Programmatic dependent launch: the kernel may start while its predecessor in the stream still runs; whatever it does before
+// pdl_wait() (barrier init, TMEM allocation, descriptor prefetch, loads of WEIGHTS) overlaps the predecessor's tail.  Every access
+// to data a predecessor produced (or still reads) comes after pdl_wait(), which returns once all prerequisite grids have completed
+// and flushed.  Kernels launched the ordinary way execute both instructions as no-ops.
+bool pdl_enabled();   // LLB_PDL=0 launches everything the ordinary way (A-B comparison)
+template <class T>
+struct pdl_ident {
+  using type = T;
+};
+template <class... KArgs>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, typename pdl_ident<KArgs>::type... args) {
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = s;
+  cfg.attrs = attr, cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
@@ -193,6 +213,9 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

@@ -364,7 +364,8 @@ static int dit_forward(llb_dit* h, int t, cudaStream_t s) {
         dit_attention_umma4_kernel<<<units < num_sms() ? units : num_sms(), ATT4_THREADS, ATT4_SMEM, s>>>(tmQKV, h->attn, h->mol_off, B, Mtok, H,
                                                                                                           L.heads, units);
       } else {
-        dit_attention_tma_kernel<<<(unsigned)(seqs * L.heads), 128, 0, s>>>(tmQKV, h->attn, h->mol_off, B, Mtok, H, L.heads);
+        LLB_CUDA_OK(launch_pdl(dit_attention_tma_kernel, dim3((unsigned)(seqs * L.heads)), dim3(128), 0, s, tmQKV, h->attn, (const int32_t*)h->mol_off, B, Mtok, H,
+                               L.heads));
       }
     }
     LLB_CUDA_OK(cudaGetLastError());

@@ -125,6 +125,8 @@ __device__ __forceinline__ uint32_t attt_swz(int row, int chunk) { return (uint3
 
 __global__ void __launch_bounds__(128) dit_attention_tma_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ out,
                                                                 const int32_t* __restrict__ mol_off, int B, int Mtok, int H, int heads) {
+  pdl_launch_dependents();
+  pdl_wait();   // qkv comes from the previous kernel of the stream
   __shared__ __align__(1024) uint8_t tiles[3 * ATTT_TILE];
   __shared__ __align__(8) uint64_t bar;
   const int head = blockIdx.x % heads;

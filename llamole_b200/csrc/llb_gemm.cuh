@@ -240,11 +240,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();   // the next kernel of the stream may begin its own prologue on SMs this grid leaves free
 
   if (warp == GEMM_EPI_WARPS) {
     // ---------------- TMA producer: the whole warp walks the ring (uniform control flow), one elected lane issues ----------------
     int stage = 0;
     uint32_t phase = 0;
+    // The WEIGHT tiles of the first ring stages do not depend on the previous kernel of the stream: they are requested before the
+    // dependency wait (programmatic dependent launch), so at small batch sizes -- where a step is a chain of ~170 short kernels,
+    // each waiting for its first weight bytes -- that latency overlaps the predecessor's tail.  Activations follow after the wait.
+    int hoisted = 0;
+    if (blockIdx.x < num_tiles) {
+      const int tile = blockIdx.x;
+      const int n0 = (m_fast ? tile / num_m : tile % num_n) * BN;
+      const int grp_i = group_n > 0 ? n0 / group_n : 0;
+      const int kw0 = group_w ? grp_i * group_k : 0, wn0 = group_w ? n0 - grp_i * group_n : n0;
+      hoisted = num_kb < STAGES ? num_kb : STAGES;
+      if (elect_one()) {
+        for (int kb = 0; kb < hoisted; ++kb) {
+          mbar_arrive_expect_tx(&full[kb], Cfg::STAGE_BYTES);
+          tma_load_2d(smB + kb * Cfg::B_BYTES, &tmB, &full[kb], kw0 + kb * GEMM_BK, wn0);
+        }
+      }
+      __syncwarp();
+    }
+    pdl_wait();
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (m_fast ? tile % num_m : tile / num_n) * GEMM_BM;
       const int n0 = (m_fast ? tile / num_m : tile % num_n) * BN;
@@ -254,12 +274,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int ka0 = grp_i * group_k;
       const int kw0 = group_w ? ka0 : 0, wn0 = group_w ? n0 - grp_i * group_n : n0;
       for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&empty[stage], phase ^ 1);
+        const bool pre = hoisted > 0;   // this stage's barrier is armed and its weight tile is on its way already
+        if (!pre) mbar_wait(&empty[stage], phase ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+          if (!pre) mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
           tma_load_2d(smA + stage * Cfg::A_BYTES, &tmA, &full[stage], ka0 + kb * GEMM_BK, m0);
-          tma_load_2d(smB + stage * Cfg::B_BYTES, &tmB, &full[stage], kw0 + kb * GEMM_BK, wn0);
+          if (!pre) tma_load_2d(smB + stage * Cfg::B_BYTES, &tmB, &full[stage], kw0 + kb * GEMM_BK, wn0);
         }
+        if (pre) --hoisted;
         __syncwarp();
         if (++stage == STAGES) {
           stage = 0;
@@ -269,6 +291,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == GEMM_EPI_WARPS + 1) {
     // ---------------- MMA issuer: converged warp, one elected lane issues (operands stay in uniform registers) ----------------
+    pdl_wait();
     const uint32_t idesc = umma_idesc_ab(GEMM_BM, BN, ab_f16 != 0);
     const uint64_t a_desc0 = umma_desc_k128(smem_u32(smA));   // stage 0, k-step 0; stages / k-steps are plain adds
     const uint64_t b_desc0 = umma_desc_k128(smem_u32(smB));
@@ -305,6 +328,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp < GEMM_EPI_WARPS) {
     // ---------------- epilogue ----------------
+    pdl_wait();   // the functor may read what the previous kernel wrote (row statistics), and C may be a buffer it still reads
     uint8_t* stg = smStage + warp * GEMM_STAGING_PER_WARP;
     int buf = 0;
     int acc = 0;
@@ -649,7 +673,8 @@ int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, in
         configured[which] = true;
       }
       ProfScope prof(ctr ? ctr->slot : LLB_PROF_GEMM_OTHER, stream);
-      kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, M, N, K, epi, grp.group_n, grp.group_k, grp.split_k ? 1 : 0, (grp.ab_f16 ? 1 : 0) | (m_fast ? 2 : 0));
+      LLB_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)Cfg::SMEM_BYTES, stream, tmA, tmB, tmC, M, N, K, epi, grp.group_n, grp.group_k,
+                             grp.split_k ? 1 : 0, (grp.ab_f16 ? 1 : 0) | (m_fast ? 2 : 0)));
       note_kernel(LLB_KERN_GEMM_1CTA);
       return LLB_OK;
     };

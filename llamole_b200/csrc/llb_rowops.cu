@@ -48,6 +48,8 @@ __device__ __forceinline__ float act_rt(float x, int act) {
 
 // Fallback for widths that are not a multiple of 128: one warp per row, three sweeps over L1/L2.
 __global__ void __launch_bounds__(256) row_ln_kernel(RowLnDev a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= a.rows) return;
@@ -114,6 +116,8 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 // Register-resident variant: the row (NCH float4 per lane, width = 128 * NCH) is read from global exactly once.
 template <int NCH, unsigned F>
 __global__ void __launch_bounds__(256) row_ln_reg_kernel(RowLnDev a) {
+  pdl_launch_dependents();   // the next kernel's prologue (and its weight prefetch) may overlap this memory-bound pass
+  pdl_wait();
   constexpr bool RT = (F & F_RUNTIME) != 0;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -219,15 +223,15 @@ __global__ void __launch_bounds__(256) row_ln_reg_kernel(RowLnDev a) {
 template <unsigned F>
 bool launch_reg(int nch, int grid, const RowLnDev& d, cudaStream_t stream) {
   switch (nch) {
-    case 1: row_ln_reg_kernel<1, F><<<grid, 256, 0, stream>>>(d); return true;
-    case 2: row_ln_reg_kernel<2, F><<<grid, 256, 0, stream>>>(d); return true;
-    case 4: row_ln_reg_kernel<4, F><<<grid, 256, 0, stream>>>(d); return true;
-    case 6: row_ln_reg_kernel<6, F><<<grid, 256, 0, stream>>>(d); return true;
-    case 8: row_ln_reg_kernel<8, F><<<grid, 256, 0, stream>>>(d); return true;
-    case 12: row_ln_reg_kernel<12, F><<<grid, 256, 0, stream>>>(d); return true;
-    case 16: row_ln_reg_kernel<16, F><<<grid, 256, 0, stream>>>(d); return true;
-    case 24: row_ln_reg_kernel<24, F><<<grid, 256, 0, stream>>>(d); return true;
-    case 32: row_ln_reg_kernel<32, F><<<grid, 256, 0, stream>>>(d); return true;
+    case 1: return launch_pdl(row_ln_reg_kernel<1, F>, dim3(grid), dim3(256), 0, stream, d) == cudaSuccess;
+    case 2: return launch_pdl(row_ln_reg_kernel<2, F>, dim3(grid), dim3(256), 0, stream, d) == cudaSuccess;
+    case 4: return launch_pdl(row_ln_reg_kernel<4, F>, dim3(grid), dim3(256), 0, stream, d) == cudaSuccess;
+    case 6: return launch_pdl(row_ln_reg_kernel<6, F>, dim3(grid), dim3(256), 0, stream, d) == cudaSuccess;
+    case 8: return launch_pdl(row_ln_reg_kernel<8, F>, dim3(grid), dim3(256), 0, stream, d) == cudaSuccess;
+    case 12: return launch_pdl(row_ln_reg_kernel<12, F>, dim3(grid), dim3(256), 0, stream, d) == cudaSuccess;
+    case 16: return launch_pdl(row_ln_reg_kernel<16, F>, dim3(grid), dim3(256), 0, stream, d) == cudaSuccess;
+    case 24: return launch_pdl(row_ln_reg_kernel<24, F>, dim3(grid), dim3(256), 0, stream, d) == cudaSuccess;
+    case 32: return launch_pdl(row_ln_reg_kernel<32, F>, dim3(grid), dim3(256), 0, stream, d) == cudaSuccess;
   }
   return false;
 }
@@ -300,7 +304,7 @@ int launch_row_ln(const RowLnArgs& a, cudaStream_t stream) {
     else if (f == V_PRED_LAST) done = launch_reg<V_PRED_LAST>(nch, grid, d, stream);
   }
   if (!done && nch > 0) done = launch_reg<F_RUNTIME>(nch, grid, d, stream);
-  if (!done) row_ln_kernel<<<grid, 256, 0, stream>>>(d);
+  if (!done) (void)launch_pdl(row_ln_kernel, dim3(grid), dim3(256), 0, stream, d);
   LLB_CUDA_OK(cudaGetLastError());
   return LLB_OK;
 }

@@ -72,6 +72,15 @@ void profile_begin(int slot, cudaStream_t s) {
 }
 void profile_end(cudaStream_t s) { cudaEventRecord(g_prof_recs.back().b, s); }
 
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("LLB_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+
 int num_sms() {
   static int sms = 0;
   if (sms == 0) {

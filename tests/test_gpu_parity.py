@@ -469,12 +469,13 @@ def test_condition_queue_matches_direct_sampling(dit, dit_small):
     ({"LLB_ATTN": "2"}, "dit_wide", "test_gpu_parity_large.py"),
     ({"LLB_FUSED_LN": "0"}, "dit_wide", "test_gpu_parity_large.py"),
     ({"LLB_GIN_FUSED_TAIL": "0"}, "gin_encoder_baseline_shape or gin_predictor_baseline_shape", "test_gpu_parity_large.py"),
+    ({"LLB_PDL": "0"}, "denoiser_logits or teacher_forced or end_to_end or gin_encoder_matches", "test_gpu_parity.py"),
 ])
 def test_kernel_variants_meet_the_same_tolerances(env, select, path):
     """Every kernel variant that an environment switch can select is held to the default path's tolerances: the tcgen05
     attention kernel (LLB_ATTN=2: P in tensor memory), the unfused GraphDiT block tails at a size where the fused ones are
-    the default (LLB_FUSED_LN=0), the GIN node MLP with a separate layer-tail row kernel (LLB_GIN_FUSED_TAIL=0).  The switches are
-    read once per process, hence the child process."""
+    the default (LLB_FUSED_LN=0), the GIN node MLP with a separate layer-tail row kernel (LLB_GIN_FUSED_TAIL=0), ordinary instead of
+    programmatic dependent launches (LLB_PDL=0).  The switches are read once per process, hence the child process."""
     import subprocess
     import sys
 

@@ -18,16 +18,21 @@ if [ -z "$quick" ]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $out/launches_$tag.csv \
       python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $out/launches_$tag.log 2>&1
   # one DiT block (qkv, attention, proj, ln, fc1, fc2, ln ...) with the full metric set
-  timeout 900 ncu --set full --clock-control none --import-source on -s 300 -c 10 -o $out/prof_dit_block_$tag -f \
+  timeout 900 ncu --set full --clock-control none -s 300 -c 8 -o $out/prof_dit_block_$tag -f \
       python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $out/ncu_block_$tag.log 2>&1
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:dit_step -s 1 -c 1 -o $out/prof_dit_step_$tag -f \
+  timeout 600 ncu --set full --clock-control none -k regex:dit_step -s 1 -c 1 -o $out/prof_dit_step_$tag -f \
       python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $out/ncu_step_$tag.log 2>&1
   # one GIN encoder layer set (aggregate, statistics GEMM, mlp0 with LayerNorm + GELU epilogue, fused GEMM + layer tail, pooling)
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:"gin_|gemm_ln_pair_kernel|gemm_tcgen05_2cta" -s 12 -c 24 -o $out/prof_gin_$tag -f \
+  timeout 600 ncu --set full --clock-control none -k regex:"gin_|gemm_ln_pair_kernel|gemm_tcgen05_2cta" -s 12 -c 12 -o $out/prof_gin_$tag -f \
       python bench.py --only gin > $out/ncu_gin_$tag.log 2>&1
   # the fused predictor head (pilot GEMM, head GEMM with the top-k epilogue, select kernel)
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:"EpiHeadTopk|gin_head_" -c 6 -o $out/prof_head_$tag -f \
+  timeout 600 ncu --set full --clock-control none -k regex:"EpiHeadTopk|gin_head_" -c 6 -o $out/prof_head_$tag -f \
       python bench.py --only predictor > $out/ncu_head_$tag.log 2>&1
   cp $out/parity.json $out/parity_$tag.json 2>/dev/null
 fi
-ls -la $out | tail -20
+# summarise on the box (the .ncu-rep files are too large to travel: gpurun_out/ is capped at 64 MiB), keep only the text
+if [ -z "$quick" ]; then
+  LLB_PROFILES_OUT=$out/profiles python tools/make_profiles.py $tag r2 > $out/make_profiles_$tag.log 2>&1
+  rm -f $out/prof_*_$tag.ncu-rep
+fi
+du -sh $out; ls -la $out | tail -20

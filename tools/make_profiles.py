@@ -11,7 +11,7 @@ import csv, gzip, io, json, os, re, shutil, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag, rnd = sys.argv[1], sys.argv[2]
 G = os.path.join(ROOT, "gpurun_out")
-P = os.path.join(ROOT, "profiles")
+P = os.environ.get("LLB_PROFILES_OUT", os.path.join(ROOT, "profiles"))   # on the GPU box: gpurun_out/profiles (only gpurun_out/ travels back)
 os.makedirs(P, exist_ok=True)
 
 
