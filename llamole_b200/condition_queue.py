@@ -127,7 +127,7 @@ class ConditionQueue:
             ns.append(n.cpu())
             pos = end
         X, E, n = torch.cat(Xs), torch.cat(Es), torch.cat(ns)
-        self._pending = [p for p in self._pending if p[0] not in set(tickets)]
+        self._pending = []      # only now: every chunk has been sampled (a failure above leaves the queue as it was)
         pos = 0
         for t in tickets:
             self._done[t] = (X[pos:pos + t.count], E[pos:pos + t.count], n[pos:pos + t.count])

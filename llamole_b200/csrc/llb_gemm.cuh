@@ -82,6 +82,16 @@ template <class E, class = void>
 struct epi_packs : std::false_type {};
 template <class E>
 struct epi_packs<E, std::void_t<decltype(E::PACKS_OUTPUT)>> : std::integral_constant<bool, E::PACKS_OUTPUT> {};
+// Functors that read per-COLUMN vectors (LayerNorm weights, biases) can have their warp's slice of up to three of them staged in
+// WARP-PRIVATE shared memory: `static constexpr int WARP_VECS = k` and `const float* warp_vec(int i) const`.  Every epilogue warp
+// loads the 128 columns it will work on (lane l: columns 4 l .. 4 l + 3 of each vector) BEFORE it waits for the tile's
+// accumulators and reads them back as broadcast LDS per chunk: one exposed L2 round trip per tile instead of one per
+// 32-column chunk (shared memory leaves this kernel next to no L1), and no barrier between warps -- a block-wide staging
+// behind a named barrier put the eight warps in lockstep and cost more than it saved.
+template <class E, class = void>
+struct epi_warp_vecs : std::integral_constant<int, 0> {};
+template <class E>
+struct epi_warp_vecs<E, std::void_t<decltype(E::WARP_VECS)>> : std::integral_constant<int, E::WARP_VECS> {};
 struct EpiNoRowState {};
 template <class E, bool HAS = epi_row_state<E>::value>
 struct epi_row_state_of { using type = EpiNoRowState; };
@@ -101,12 +111,44 @@ __device__ __forceinline__ typename epi_row_state_of<Epi>::type gemm_epilogue_ro
   }
 }
 
+// per-warp staging area: a ring of 32-row output boxes, minus 2 KB for the staged column vectors of functors that ask for them
+template <class Epi>
+struct GemmWarpStaging {
+  static constexpr int NV = epi_warp_vecs<Epi>::value;
+  static constexpr int RING_BYTES = NV > 0 ? GEMM_STAGING_PER_WARP - 2048 : GEMM_STAGING_PER_WARP;
+  static_assert(NV <= 3, "at most three staged vectors (3 x 128 floats = 1.5 KB per warp)");
+};
+// this warp's 128-column slices of the functor's vectors -> its private shared memory (call before waiting for the accumulators)
+template <int BN, class Epi>
+__device__ __forceinline__ void gemm_stage_warp_vectors(const Epi& epi, uint8_t* stg, int n0, int N) {
+  constexpr int NV = epi_warp_vecs<Epi>::value;
+  if constexpr (NV > 0) {
+    constexpr int COLS_PER_WARP = BN / (GEMM_EPI_WARPS / 4);
+    static_assert(COLS_PER_WARP == 128, "warp-staged vectors assume 128 columns per epilogue warp");
+    const int lane = threadIdx.x & 31, cg = uniform_warp_idx() >> 2;
+    const uint32_t wv = smem_u32(stg) + GemmWarpStaging<Epi>::RING_BYTES;
+    const int col = n0 + cg * COLS_PER_WARP + 4 * lane;
+    __syncwarp();   // the previous tile's reads of this area are done
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float* src = epi.warp_vec(i);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (col + 3 < N) v = __ldg(reinterpret_cast<const float4*>(src + col));
+      else if (col < N) v = make_float4(__ldg(src + col), col + 1 < N ? __ldg(src + col + 1) : 0.f, col + 2 < N ? __ldg(src + col + 2) : 0.f, 0.f);
+      sts128(wv + (i * COLS_PER_WARP + 4 * lane) * 4, v);
+    }
+    __syncwarp();
+  }
+}
+
 template <int BN, bool TMA_STORE, class Epi>
 __device__ __forceinline__ void gemm_epilogue_tile(const Epi& epi, const CUtensorMap* tmC, uint32_t tmem_acc, int m0, int n0, int M,
                                                    int N, uint8_t* stg, int& buf, typename epi_row_state_of<Epi>::type rst) {
   constexpr int ELEM = Epi::OUT_F32 ? 4 : 2;
   constexpr int ROW_BYTES = Epi::CHUNK * ELEM;
-  constexpr int NBUF = GEMM_STAGING_PER_WARP / (32 * ROW_BYTES);
+  constexpr int NBUF = GemmWarpStaging<Epi>::RING_BYTES / (32 * ROW_BYTES);
+  constexpr bool WV = epi_warp_vecs<Epi>::value > 0;
+  static_assert(NBUF >= 1, "staging ring too small for this epilogue");
   constexpr int COLS_PER_WARP = BN / (GEMM_EPI_WARPS / 4);
   constexpr bool ROW_STATE = epi_row_state<Epi>::value;
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
@@ -125,7 +167,9 @@ __device__ __forceinline__ void gemm_epilogue_tile(const Epi& epi, const CUtenso
     if (Epi::CHUNK == 64) tmem_ld32(t_row + c + 32, v + 32);
     tmem_ld_wait();
     if (!LLB_EXP(4)) {
-      if constexpr (PACKS) {
+      if constexpr (PACKS && WV) {
+        epi.transform_pack(row, col0, v, packed, M, N, rst, smem_u32(stg) + GemmWarpStaging<Epi>::RING_BYTES + c * 4);
+      } else if constexpr (PACKS) {
         if constexpr (ROW_STATE) epi.transform_pack(row, col0, v, packed, M, N, rst);
         else epi.transform_pack(row, col0, v, packed, M, N);
       } else if constexpr (ROW_STATE) {
@@ -337,6 +381,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int m0 = (m_fast ? tile % num_m : tile / num_n) * GEMM_BM;
       const int n0 = (m_fast ? tile / num_m : tile % num_n) * BN;
       const auto rst = gemm_epilogue_row_begin(epi, m0, M);
+      gemm_stage_warp_vectors<BN>(epi, stg, n0, N);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       gemm_epilogue_tile<BN, TMA_STORE>(epi, &tmC, tmem_base + acc * BN, m0, n0, M, N, stg, buf, rst);
@@ -571,6 +616,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const int n0 = (m_fast ? tile / num_m : tile % num_n) * BN;
       if (warp == 0 && lane == 0) LLB_TRACE(tcount, 6, clock64());
       const auto rst = gemm_epilogue_row_begin(epi, m0, M);
+      gemm_stage_warp_vectors<BN>(epi, stg, n0, N);
       mbar_wait(&tmem_full[acc], acc_phase);
       if (warp == 0 && lane == 0) LLB_TRACE(tcount, 7, clock64());
       tc_fence_after();

@@ -23,10 +23,10 @@ if [ -z "$quick" ]; then
   timeout 600 ncu --set full --clock-control none -k regex:dit_step -s 1 -c 1 -o $out/prof_dit_step_$tag -f \
       python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $out/ncu_step_$tag.log 2>&1
   # one GIN encoder layer set (aggregate, statistics GEMM, mlp0 with LayerNorm + GELU epilogue, fused GEMM + layer tail, pooling)
-  timeout 600 ncu --set full --clock-control none -k regex:"gin_|gemm_ln_pair_kernel|gemm_tcgen05_2cta" -s 12 -c 12 -o $out/prof_gin_$tag -f \
+  timeout 600 ncu --set full --clock-control none --kernel-name-base demangled -k regex:"gin_aggregate|gin_pool|gemm_ln_pair_kernel|EpiRowSq|EpiLnGelu" -s 12 -c 12 -o $out/prof_gin_$tag -f \
       python bench.py --only gin > $out/ncu_gin_$tag.log 2>&1
   # the fused predictor head (pilot GEMM, head GEMM with the top-k epilogue, select kernel)
-  timeout 600 ncu --set full --clock-control none -k regex:"EpiHeadTopk|gin_head_" -c 6 -o $out/prof_head_$tag -f \
+  timeout 600 ncu --set full --clock-control none --kernel-name-base demangled -k regex:"EpiHeadTopk|gin_head_" -c 6 -o $out/prof_head_$tag -f \
       python bench.py --only predictor > $out/ncu_head_$tag.log 2>&1
   cp $out/parity.json $out/parity_$tag.json 2>/dev/null
 fi

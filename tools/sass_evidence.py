@@ -26,7 +26,9 @@ for k, d in zip(names, dem):
     c = counts[k]
     if not c:
         continue
-    name = re.sub(r"\(.*", "", d).replace("llb::", "").replace("(anonymous namespace)::", "").replace("void ", "")
+    d = d.replace("(anonymous namespace)::", "").replace("llb::", "").replace("void ", "")
+    d = re.sub(r"\((bool|int|unsigned int)\)", "", d)
+    name = re.sub(r"\(.*", "", d)
     out.append(f"{name[:100]:100s} " + " ".join(f"{a}={b}" for a, b in sorted(c.items())))
 path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", f"{rnd}_sass_evidence.txt")
 open(path, "w").write("\n".join(out) + "\n")
