@@ -195,6 +195,11 @@ int llb_dit_sample(llb_dit* h, int t_first, int t_last, uint64_t seed, const flo
                    llb_stream_t stream);
 /* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */
 int64_t llb_dit_launch_count(const llb_dit* h);
+/* Small batches (fewer than 2048 token rows, e.g. the reference's per-prompt batches of 6, modeling_llamole.py:653): from the
+ * second denoiser pass of a batch binding on, the t-independent launches of a pass are replayed as one CUDA graph (a launch
+ * count still reports the kernels executed).  1 = the graph is in use, 0 = not built (large batch, first pass, profiling on,
+ * LLB_GRAPH=0), -1 = capture or instantiation failed and the pass is issued launch by launch. */
+int llb_dit_graph_state(const llb_dit* h);
 
 /* Standalone fused posterior + guidance + sampling (K8-K10) from given dense masked logits; used by the
  * parity tests to check categories bit-exactly against the oracle on identical logits and noise. */

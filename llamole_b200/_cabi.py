@@ -84,6 +84,7 @@ SIGNATURES = {
     "llb_dit_step": (_I, [_P, _I, C.c_uint64, _P, _P, _P, _P, _P]),
     "llb_dit_sample": (_I, [_P, _I, _I, C.c_uint64, _P, _P, _P]),
     "llb_dit_launch_count": (C.c_int64, [_P]),
+    "llb_dit_graph_state": (C.c_int, [_P]),
     "llb_dit_posterior_sample": (_I, [_P, _I, _P, _P, _P, _P, C.c_uint64, _P, _P, _P, _P, _P]),
     "llb_gin_packed_bytes": (_I, [C.POINTER(GinConfig), C.POINTER(_SZ)]),
     "llb_gin_pack_weights": (_I, [C.POINTER(GinConfig), C.POINTER(GinWeights), _P, _SZ, _P]),

@@ -56,7 +56,7 @@ struct ProfScope {
   }
 };
 
-void note_kernel(int family);   // llb_kernel_launches counters
+void note_kernel(int family, int64_t n = 1);   // llb_kernel_launches counters (n < 0: a stream capture issued nothing)
 
 // Programmatic dependent launch: the kernel may start while its predecessor in the stream still runs; whatever it does before
 // pdl_wait() (barrier init, TMEM allocation, descriptor prefetch, loads of WEIGHTS) overlaps the predecessor's tail.  Every access

@@ -222,6 +222,22 @@ struct llb_dit {
   int32_t* row_mol = nullptr;    // (Mtok)
   int32_t* row_group = nullptr;  // (M): modulation row of each token row
   void* ln_sync = nullptr;       // statistics-exchange workspace of the CTA-pair GEMM + LayerNorm kernel
+  // Latency regime: everything of a denoiser pass that does not depend on t (all but the conditioning-vector kernel) is captured
+  // once per batch binding and replayed as ONE CUDA graph launch; the programmatic-dependent-launch edges are kept by the capture.
+  cudaGraphExec_t body_graph = nullptr;
+  cudaStream_t capture_stream = nullptr;
+  int graph_state = 0;           // 0 not built, 1 ready, -1 capture / instantiation failed for this binding (eager launches)
+  int passes_run = 0;            // denoiser passes since llb_dit_begin (the first one runs eagerly: lazy one-time set-up is not capturable)
+  int64_t graph_launches = 0;    // kernel launches one replay stands for
+  int64_t graph_kern[LLB_KERN_FAMILIES] = {};
+  void drop_graph() {
+    if (body_graph) cudaGraphExecDestroy(body_graph);
+    body_graph = nullptr, graph_state = 0, passes_run = 0;
+  }
+  ~llb_dit() {
+    drop_graph();
+    if (capture_stream) cudaStreamDestroy(capture_stream);
+  }
   template <class T>
   const T* w(size_t off) const { return reinterpret_cast<const T*>(blob + off); }
 };
@@ -264,12 +280,17 @@ static int dit_carve(llb_dit* h, void* ws, size_t ws_bytes, int B, int Mtok, siz
   return LLB_OK;
 }
 
-// One full denoiser pass over both CFG halves up to the raw output-layer rows (h->raw).
-static int dit_forward(llb_dit* h, int t, cudaStream_t s) {
+static bool dit_latency_regime(const llb_dit* h) {
+  static const bool ln_env_set = getenv("LLB_FUSED_LN") != nullptr;
+  return !ln_env_set && h->passes * h->Mtok < 2048;
+}
+
+// The t-independent part of a denoiser pass: token embedding, every adaLN modulation (from h->cvec), the transformer blocks and the
+// output MLP, up to the raw output-layer rows (h->raw).
+static int dit_body(llb_dit* h, cudaStream_t s) {
   const DitLayout& L = h->L;
   const int H = L.H, F = L.F, D = L.D, B = h->B, Mtok = h->Mtok;
   const int M = h->passes * Mtok;
-  if (Mtok == 0) return LLB_OK;
   GemmCounters* ctr = &h->ctr;
   // 1. tokens -> embedding -> LayerNorm (shared by both halves)
   {
@@ -291,14 +312,7 @@ static int dit_forward(llb_dit* h, int t, cudaStream_t s) {
     LLB_TRY(launch_row_ln(a, s));
     h->launches++;
   }
-  // 2. conditioning vector and all adaLN modulations of this step
-  {
-    ProfScope prof(LLB_PROF_DIT_MISC, s);
-    dit_cvec_kernel<<<ceil_div((B + 1) * H, 256), 256, 0, s>>>(h->w<float>(L.c1_table) + (size_t)t * H, h->cinv, h->w<float>(L.c_unc),
-                                                            h->cvec, B, H);
-  }
-  LLB_CUDA_OK(cudaGetLastError());
-  h->launches++;
+  // 2. all adaLN modulations of this step from the conditioning vector
   ctr->slot = LLB_PROF_GEMM_ADALN;
   const int ldh = (D + 1) * H;
   LLB_TRY(gemm_bias_act(h->cvec, H, h->w<void>(L.ada0_w), H, h->w<float>(L.ada0_b), h->hid, ldh, B + 1, ldh, H, LLB_ACT_SILU, false, s, ctr));
@@ -326,8 +340,7 @@ static int dit_forward(llb_dit* h, int t, cudaStream_t s) {
   // fused block tails occupy only 2 M / 256 row groups of 8 SMs each and stream their weights through too few TMA rings
   // (fc2 + LN 33 us vs 19 + 9 us for GEMM<64> + row kernel at 406 rows), so the unfused pair is used unless
   // LLB_FUSED_LN says otherwise.  Measured cross-over: 978 rows 2.54 vs 3.06 ms/step, 3870 rows 4.45 vs 4.20.
-  static const bool ln_env_set = getenv("LLB_FUSED_LN") != nullptr;
-  const bool latency_regime = !ln_env_set && M < 2048;
+  const bool latency_regime = dit_latency_regime(h);
   const bool fused_ln = gemm_ln_supported(H, H) && gemm_ln_supported(H, F) && gemm_ln_enabled() && !latency_regime;
   // LLB_FUSED_LN=0: GEMM + row kernel everywhere; default: both block halves fused on the CTA-pair kernel when H = 1024
   // (other widths have no fused kernel: a full row must fit four pairs' tensor memory).
@@ -353,7 +366,11 @@ static int dit_forward(llb_dit* h, int t, cudaStream_t s) {
     const bool share0 = l == 0 && h->passes == 2 && fused_ln;
     ctr->slot = LLB_PROF_GEMM_QKV;
     EpiQKV eq{h->qkv, 3 * H, H, h->w<float>(L.qn_w[l]), h->w<float>(L.qn_b[l]), h->w<float>(L.kn_w[l]), h->w<float>(L.kn_b[l]), q_scale};
-    LLB_TRY((launch_gemm<256>(h->xb, H, h->w<void>(L.qkv_w[l]), H, share0 ? Mtok : M, 3 * H, H, eq, s, ctr)));
+    // latency regime: 128-wide tiles while they fit one wave (twice the CTAs streaming the weight, half the MMAs per CTA)
+    if (latency_regime && ceil_div(M, 128) * ceil_div(3 * H, 128) <= num_sms())
+      LLB_TRY((launch_gemm<128>(h->xb, H, h->w<void>(L.qkv_w[l]), H, M, 3 * H, H, eq, s, ctr)));
+    else
+      LLB_TRY((launch_gemm<256>(h->xb, H, h->w<void>(L.qkv_w[l]), H, share0 ? Mtok : M, 3 * H, H, eq, s, ctr)));
     {
       const int seqs = (share0 ? 1 : h->passes) * B;
       CUtensorMap tmQKV;
@@ -427,6 +444,69 @@ static int dit_forward(llb_dit* h, int t, cudaStream_t s) {
   LLB_TRY(gemm_bias_act(h->xb, H, h->w<void>(L.out_fc1_w), H, h->w<float>(L.out_fc1_b), h->y, H, M, H, H, LLB_ACT_GELU, false, s, ctr));
   LLB_TRY(gemm_bias_act(h->y, H, h->w<void>(L.out_fc2_w), H, h->w<float>(L.out_fc2_b), h->raw, h->raw_ld, M, L.d0, H, LLB_ACT_NONE, true, s, ctr));
   return LLB_OK;
+}
+
+static bool dit_graph_enabled() {
+  static const bool on = !(getenv("LLB_GRAPH") && getenv("LLB_GRAPH")[0] == '0');
+  return on;
+}
+
+// Capture dit_body on the handle's own stream (the caller's may be the legacy default stream, which cannot be captured) and
+// instantiate it; the executable graph is then launched into the caller's stream.
+static int dit_build_graph(llb_dit* h) {
+  h->graph_state = -1;
+  if (!h->capture_stream) LLB_CUDA_OK(cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking));
+  int64_t kern0[LLB_KERN_FAMILIES];
+  for (int f = 0; f < LLB_KERN_FAMILIES; ++f) kern0[f] = llb_kernel_launches(f);
+  const int64_t own0 = h->launches, gemm0 = h->ctr.launches;
+  LLB_CUDA_OK(cudaStreamBeginCapture(h->capture_stream, cudaStreamCaptureModeThreadLocal));
+  const int rc = dit_body(h, h->capture_stream);
+  cudaGraph_t g = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(h->capture_stream, &g);
+  // the capture issued nothing: take its launches back out of the counters, replays add them
+  h->graph_launches = (h->launches - own0) + (h->ctr.launches - gemm0);
+  h->launches = own0, h->ctr.launches = gemm0;
+  for (int f = 0; f < LLB_KERN_FAMILIES; ++f) {
+    h->graph_kern[f] = llb_kernel_launches(f) - kern0[f];
+    note_kernel(f, -h->graph_kern[f]);
+  }
+  if (rc != LLB_OK || e != cudaSuccess || !g) {
+    if (g) cudaGraphDestroy(g);
+    (void)cudaGetLastError();
+    return rc != LLB_OK ? rc : LLB_OK;   // an un-capturable launch is not an error of the pass: it runs eagerly
+  }
+  const cudaError_t ei = cudaGraphInstantiate(&h->body_graph, g, 0);
+  cudaGraphDestroy(g);
+  if (ei != cudaSuccess) {
+    (void)cudaGetLastError();
+    h->body_graph = nullptr;
+    return LLB_OK;
+  }
+  h->graph_state = 1;
+  return LLB_OK;
+}
+
+// One full denoiser pass over both CFG halves up to the raw output-layer rows (h->raw).
+static int dit_forward(llb_dit* h, int t, cudaStream_t s) {
+  const DitLayout& L = h->L;
+  if (h->Mtok == 0) return LLB_OK;
+  {
+    ProfScope prof(LLB_PROF_DIT_MISC, s);
+    dit_cvec_kernel<<<ceil_div((h->B + 1) * L.H, 256), 256, 0, s>>>(h->w<float>(L.c1_table) + (size_t)t * L.H, h->cinv, h->w<float>(L.c_unc),
+                                                                  h->cvec, h->B, L.H);
+  }
+  LLB_CUDA_OK(cudaGetLastError());
+  h->launches++;
+  const bool want_graph = dit_latency_regime(h) && dit_graph_enabled() && !profile_on() && h->passes_run >= 1;
+  h->passes_run++;
+  if (want_graph && h->graph_state == 0) LLB_TRY(dit_build_graph(h));
+  if (want_graph && h->graph_state == 1) {
+    LLB_CUDA_OK(cudaGraphLaunch(h->body_graph, s));
+    h->launches += h->graph_launches;
+    for (int f = 0; f < LLB_KERN_FAMILIES; ++f) note_kernel(f, h->graph_kern[f]);
+    return LLB_OK;
+  }
+  return dit_body(h, s);
 }
 
 static int dit_launch_step(llb_dit* h, DitStepArgs& a, cudaStream_t s) {
@@ -600,6 +680,7 @@ int llb_dit_begin(llb_dit* h, void* workspace, size_t workspace_bytes, int B, co
   size_t need = 0;
   LLB_TRY(dit_carve(h, workspace, workspace_bytes, B, Mtok, &need));
   if (need > workspace_bytes) return fail(LLB_ERR_WORKSPACE, "dit: workspace needs %zu bytes, got %zu", need, workspace_bytes);
+  h->drop_graph();   // the captured launches carry the previous binding's pointers and sizes
   h->B = B, h->Mtok = Mtok, h->mol_base = mol_index_base;
   std::vector<int32_t> row_mol(Mtok > 0 ? Mtok : 1), row_group(h->passes * Mtok > 0 ? h->passes * Mtok : 1);
   for (int b = 0; b < B; ++b)
@@ -693,6 +774,8 @@ int llb_dit_sample(llb_dit* h, int t_first, int t_last, uint64_t seed, const flo
 }
 
 int64_t llb_dit_launch_count(const llb_dit* h) { return h ? h->launches + h->ctr.launches : 0; }
+
+int llb_dit_graph_state(const llb_dit* h) { return h ? h->graph_state : 0; }
 
 int llb_dit_posterior_sample(llb_dit* h, int t, const float* lc_X, const float* lc_E, const float* lu_X,
                              const float* lu_E, uint64_t seed, const float* qX, const float* qE, float* prob_X,

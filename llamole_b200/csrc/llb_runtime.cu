@@ -25,8 +25,8 @@ int fail(int code, const char* fmt, ...) {
 }
 
 static int64_t g_kernel_launches[LLB_KERN_FAMILIES];
-void note_kernel(int family) {
-  if (family >= 0 && family < LLB_KERN_FAMILIES) __atomic_add_fetch(&g_kernel_launches[family], 1, __ATOMIC_RELAXED);
+void note_kernel(int family, int64_t n) {
+  if (family >= 0 && family < LLB_KERN_FAMILIES) __atomic_add_fetch(&g_kernel_launches[family], n, __ATOMIC_RELAXED);
 }
 
 // ---- live profiling -------------------------------------------------------------------------------

@@ -410,6 +410,10 @@ class _DitEngine:
     def launch_count(self) -> int:
         return int(self.lib.llb_dit_launch_count(self.handle))
 
+    def graph_state(self) -> int:
+        """1 when the t-independent launches of a reverse step are replayed as a CUDA graph (small batches), see the header."""
+        return int(self.lib.llb_dit_graph_state(self.handle))
+
 
 def state_from_onehot(X: torch.Tensor, E: torch.Tensor):
     """One-hot (B,N,16)/(B,N,N,5) reference tensors -> int8 class state (-1 where the vector is all zero)."""

@@ -470,12 +470,13 @@ def test_condition_queue_matches_direct_sampling(dit, dit_small):
     ({"LLB_FUSED_LN": "0"}, "dit_wide", "test_gpu_parity_large.py"),
     ({"LLB_GIN_FUSED_TAIL": "0"}, "gin_encoder_baseline_shape or gin_predictor_baseline_shape", "test_gpu_parity_large.py"),
     ({"LLB_PDL": "0"}, "denoiser_logits or teacher_forced or end_to_end or gin_encoder_matches", "test_gpu_parity.py"),
+    ({"LLB_GRAPH": "0"}, "denoiser_logits or teacher_forced or end_to_end or degenerate", "test_gpu_parity.py"),
 ])
 def test_kernel_variants_meet_the_same_tolerances(env, select, path):
     """Every kernel variant that an environment switch can select is held to the default path's tolerances: the tcgen05
     attention kernel (LLB_ATTN=2: P in tensor memory), the unfused GraphDiT block tails at a size where the fused ones are
     the default (LLB_FUSED_LN=0), the GIN node MLP with a separate layer-tail row kernel (LLB_GIN_FUSED_TAIL=0), ordinary instead of
-    programmatic dependent launches (LLB_PDL=0).  The switches are read once per process, hence the child process."""
+    programmatic dependent launches (LLB_PDL=0), launch-by-launch instead of graph-replayed small-batch passes (LLB_GRAPH=0).  The switches are read once per process, hence the child process."""
     import subprocess
     import sys
 
@@ -714,6 +715,60 @@ def test_sampler_is_deterministic_on_the_fused_throughput_path():
     X, E = eng.get_state()
     torch.cuda.synchronize()
     assert torch.equal(X, ref[0][cut:]) and torch.equal(E, ref[1][cut:])
+
+
+def test_small_batch_graph_replay_is_bit_identical_to_eager_launches():
+    """Latency regime (the reference samples the 6 prompts of a dataloader batch, modeling_llamole.py:653): from the second
+    denoiser pass of a batch binding on, the t-independent launches are replayed as one CUDA graph.  The replay must be in use
+    (graph_state 1), must give the same integer graphs and logits as launch-by-launch execution (live profiling forces that),
+    must count the kernels it executes, and a new binding of another size must rebuild it."""
+    from llamole_b200 import _cabi
+
+    cfg = synth.dit_config(hidden=1024, depth=2, heads=16)
+    meta = synth.dit_meta(50)
+    d = tempfile.mkdtemp()
+    synth.write_dit_checkpoint(d, cfg, meta, synth.dit_state_dict(cfg, 50, seed=98))
+    m = GraphDiT(os.path.join(d, "config.yaml"), os.path.join(d, "data.meta.json"), torch.float32)
+    m.init_model(d)
+    m.disable_grads()
+    m = m.to(DEV)
+    T = cfg["diffusion_steps"]
+    eng = m.engine()
+    if os.environ.get("LLB_GRAPH") == "0":
+        pytest.skip("graph replay switched off")
+    out = {}
+    for B in (6, 16, 6):
+        props, txt = synth.dit_conditions(B, seed=40 + B)
+        props = torch.where(props == -200.0, torch.full_like(props, float("nan")), props).to(DEV).contiguous()
+        n_nodes = torch.randint(8, 51, (B,), dtype=torch.int32, generator=torch.Generator().manual_seed(B))
+        res = []
+        for eager in (False, True):
+            _cabi.profile_enable(eager)
+            try:
+                eng.begin(n_nodes, props, txt.to(DEV).contiguous())
+                eng.init_state(13, None, None)
+                l0 = eng.launch_count()
+                per_step = []
+                for i in range(5):
+                    eng.step(T - i, 13)
+                    per_step.append(eng.launch_count() - l0)
+                    l0 = eng.launch_count()
+                lX, lE = eng.denoise(T - 5, False)
+                X, E = eng.get_state()
+                torch.cuda.synchronize()
+                state = eng.graph_state()
+            finally:
+                _cabi.profile_enable(False)
+            assert state == (0 if eager else 1), f"B={B} eager={eager}: graph_state {state}"
+            assert len(set(per_step)) == 1, f"launch count per step changes between eager and replayed passes: {per_step}"
+            res.append((X.clone(), E.clone(), lX.clone(), lE.clone(), per_step[0]))
+        g, e = res
+        assert torch.equal(g[0], e[0]) and torch.equal(g[1], e[1]), f"B={B}: sampled graphs differ between replay and eager launches"
+        assert torch.equal(g[2], e[2]) and torch.equal(g[3], e[3]), f"B={B}: logits differ between replay and eager launches"
+        assert g[4] == e[4]
+        out.setdefault(B, []).append(g)
+    # the second binding of B=6 (after B=16 invalidated the graph) reproduces the first
+    assert torch.equal(out[6][0][0], out[6][1][0]) and torch.equal(out[6][0][2], out[6][1][2])
 
 
 def test_gin_rejects_out_of_range_inputs_like_the_reference():
