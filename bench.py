@@ -289,6 +289,7 @@ def main():
     # ------------------------------------------------------------------ GraphDiT
     m, cfg, meta, sd = build_dit(device, small=args.small)
     eng = m.engine()
+    latency = bench_latency(args, m, eng, device, local_rank, pk, T)
     B = args.dit_batch
     N = m.max_n_nodes
     props_h, txt_h = synth.dit_conditions(B, seed=2024 + rank)
@@ -414,33 +415,6 @@ def main():
                   "mean_atoms": float(n_rag.double().mean()), "tokens_per_pass": int(n_rag.sum()),
                   "achieved_tflops": rag_flops / (rag_ms / 1e3) / 1e12, "frac_of_sustained": rag_flops / (rag_ms / 1e3) / (pk["tf_sustained"] * 1e12),
                   "note": "node counts ~ the (synthetic) checkpoint histogram, uniform on 5..N; varlen packing: only valid atoms are computed"}
-    # ------------------------------------------------------------------ latency regime (BASELINE.json configs[0]: B = 16; the
-    # reference's own call pattern: B = 6 = per_device_eval_batch_size of config/generate/*.yaml, modeling_llamole.py:653)
-    latency = None
-    if not args.small:
-        weight_bytes = sum(p.numel() for n_, p in m.denoiser.named_parameters() if p.dim() == 2) * 2    # bf16 GEMM operands streamed once per step
-        floor_ms = weight_bytes / (pk["hbm"] * 1e9) * 1e3
-        latency = {"weight_bytes": weight_bytes, "weight_streaming_floor_ms": floor_ms, "batches": {}}
-        for Bl in (6, 16):
-            pl, tl = synth.dit_conditions(Bl, seed=900 + Bl)
-            pl = torch.where(pl == -200.0, torch.full_like(pl, float("nan")), pl).to(device).contiguous()
-            n_l = m.sample_n_nodes(Bl, generator=torch.Generator().manual_seed(5 + Bl)).clamp_(min=10)
-            eng.begin(n_l.to(torch.int32), pl, tl.to(device).contiguous(), mol_index_base=0)
-            eng.init_state(7, None, None)
-            for i in range(5):
-                eng.step(T - i, 7)
-            torch.cuda.synchronize()
-            k_lat = 50
-            ev0.record()
-            for i in range(k_lat):
-                eng.step(T - 5 - i, 7)
-            ev1.record()
-            torch.cuda.synchronize()
-            ms_l = ev0.elapsed_time(ev1) / k_lat
-            latency["batches"][str(Bl)] = {"ms_per_step": ms_l, "molecules_per_s": Bl / (T * ms_l / 1e3), "token_rows": 2 * int(n_l.sum()),
-                                           "floor_frac": floor_ms / ms_l, "steps": k_lat}
-        latency["note"] = ("one reverse step (cond + uncond pass batched, posterior, sampling) at the reference's per-prompt batch sizes; "
-                           "floor = streaming the bf16 weights once per step at the measured HBM peak")
     # ------------------------------------------------------------------ GIN encoder
     gin = bench_gin(args, device, rank, world, barrier, max_over_ranks, pk)
     pred = None
@@ -617,6 +591,41 @@ def bench_predictor(args, device, rank, world, barrier, max_over_ranks, pk):
     del m, eng
     torch.cuda.empty_cache()
     return out
+
+
+def bench_latency(args, m, eng, device, local_rank, pk, T):
+    """Latency regime (BASELINE.json configs[0]: B = 16; the reference's own call pattern: B = 6 = per_device_eval_batch_size of
+    config/generate/*.yaml, modeling_llamole.py:653).  Measured BEFORE the throughput section: a handful of molecules never reaches
+    the power cap, so the SM clock of this measurement should not be the capped one the long step leaves behind."""
+    if args.small:
+        return None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    weight_bytes = sum(p.numel() for n_, p in m.denoiser.named_parameters() if p.dim() == 2) * 2    # bf16 GEMM operands streamed once per step
+    floor_ms = weight_bytes / (pk["hbm"] * 1e9) * 1e3
+    latency = {"weight_bytes": weight_bytes, "weight_streaming_floor_ms": floor_ms, "batches": {}}
+    for Bl in (6, 16):
+        pl, tl = synth.dit_conditions(Bl, seed=900 + Bl)
+        pl = torch.where(pl == -200.0, torch.full_like(pl, float("nan")), pl).to(device).contiguous()
+        n_l = m.sample_n_nodes(Bl, generator=torch.Generator().manual_seed(5 + Bl)).clamp_(min=10)
+        eng.begin(n_l.to(torch.int32), pl, tl.to(device).contiguous(), mol_index_base=0)
+        eng.init_state(7, None, None)
+        for i in range(20):
+            eng.step(T - i, 7)
+        torch.cuda.synchronize()
+        k_lat = 200
+        with ClockSampler(local_rank) as clk:
+            ev0.record()
+            for i in range(k_lat):
+                eng.step(T - 20 - i, 7)
+            ev1.record()
+            torch.cuda.synchronize()
+        ms_l = ev0.elapsed_time(ev1) / k_lat
+        latency["batches"][str(Bl)] = {"ms_per_step": ms_l, "molecules_per_s": Bl / (T * ms_l / 1e3), "token_rows": 2 * int(n_l.sum()),
+                                       "floor_frac": floor_ms / ms_l, "steps": k_lat, "graph_replay": eng.graph_state() == 1,
+                                       "sm_mhz": clk.summary().get("sm_mhz")}
+    latency["note"] = ("one reverse step (cond + uncond pass batched, posterior, sampling) at the reference's per-prompt batch sizes, measured "
+                       "before the throughput section; floor = streaming the bf16 weights once per step at the measured HBM peak")
+    return latency
 
 
 def bench_gin(args, device, rank, world, barrier, max_over_ranks, pk):

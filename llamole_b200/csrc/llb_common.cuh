@@ -214,6 +214,27 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+#ifdef LLB_STEP_TRACE
+// Debug-only timeline of the latency regime (tools/step_trace.py builds the library with -DLLB_STEP_TRACE; never in the product
+// build): CTA 0 of every kernel appends {tag, info, globaltimer} records; one buffer pointer per translation unit.
+static __device__ unsigned long long* g_step_trace;
+__device__ __forceinline__ void step_stamp(unsigned long long tag, unsigned long long info) {
+  unsigned long long* t = g_step_trace;
+  if (t) {
+    const unsigned long long i = atomicAdd(t, 1ull);
+    if (i < 20000) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      t[1 + 3 * i] = tag, t[2 + 3 * i] = info, t[3 + 3 * i] = now;
+    }
+  }
+}
+#define LLB_STAMP(tag, info, cond) do { if (blockIdx.x == 0 && (cond)) step_stamp((tag), (info)); } while (0)
+#define LLB_STEP_TRACE_INSTALL(name) extern "C" int name(void* p) { return cudaMemcpyToSymbol(llb::g_step_trace, &p, sizeof(p)) == cudaSuccess ? 0 : 1; }
+#else
+#define LLB_STAMP(tag, info, cond) do { } while (0)
+#define LLB_STEP_TRACE_INSTALL(name)
+#endif
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
@@ -271,6 +292,10 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+__device__ __forceinline__ void l2_prefetch_tile(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1)
+               : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");

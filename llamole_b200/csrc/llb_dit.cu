@@ -77,7 +77,7 @@ int make_layout(const llb_dit_config& c, DitLayout& L) {
   for (size_t l = 0; l < D; ++l) {
     L.qn_w.push_back(take(DIT_DH * 4)), L.qn_b.push_back(take(DIT_DH * 4));
     L.kn_w.push_back(take(DIT_DH * 4)), L.kn_b.push_back(take(DIT_DH * 4));
-    L.proj_b.push_back(take(H * 4)), L.fc1_b.push_back(take(F * 4));
+    L.proj_b.push_back(take(2 * H * 4)), L.fc1_b.push_back(take(F * 4));   // proj: H values, then zeros (bias of the 2-slice split-K launch)
     L.fc2_b.push_back(take(LLB_DIT_SPLITK * H * 4));   // H values, then zeros: bias of the split-K launch (slice 0 carries it)
   }
   for (size_t l = 0; l < D; ++l) L.ada2_b.push_back(take(6 * H * 4));   // contiguous, like the weights
@@ -404,9 +404,23 @@ static int dit_body(llb_dit* h, cudaStream_t s) {
         LLB_TRY(launch_gemm_ln_pair(h->attn, H, h->w<void>(L.proj_w[l]), H, rows, H, H, fp, h->ln_sync, ln_sync_bytes, s, ctr));
       }
     } else {
-      LLB_TRY(gemm_bias_act(h->attn, H, h->w<void>(L.proj_w[l]), H, h->w<float>(L.proj_b[l]), h->y, H, M, H, H, LLB_ACT_NONE, false, s, ctr));
-      a.shift = mod, a.scale = mod + H, a.gate = mod + 2 * H;
-      LLB_TRY(launch_row_ln(a, s));
+      // latency regime: K = H in two slices (twice the CTAs streaming the weight, half the k-blocks each: the k-loop is paced by
+      // the bytes one SM's TMA ring can take, 406 rows: 16 blocks 3.0 us), partial products summed by the row kernel
+      static const bool no_splitk_p = getenv("LLB_SPLITK") && getenv("LLB_SPLITK")[0] == '0';
+      if (latency_regime && !no_splitk_p && M <= 640 && H % 128 == 0 && ceil_div(M, 128) * (2 * H / 64) <= num_sms()) {
+        GemmGroups grp;
+        grp.group_n = H, grp.group_k = H / 2, grp.split_k = true;
+        LLB_TRY(gemm_bias_act(h->attn, H, h->w<void>(L.proj_w[l]), H, h->w<float>(L.proj_b[l]), h->part, 2 * H, M, 2 * H, H / 2, LLB_ACT_NONE, true, s,
+                              ctr, grp));
+        RowLnArgs ap = a;
+        ap.in = h->part, ap.in_ld = 2 * H, ap.in_bf16 = false, ap.in_parts = 2, ap.in_part_stride = H;
+        ap.shift = mod, ap.scale = mod + H, ap.gate = mod + 2 * H;
+        LLB_TRY(launch_row_ln(ap, s));
+      } else {
+        LLB_TRY(gemm_bias_act(h->attn, H, h->w<void>(L.proj_w[l]), H, h->w<float>(L.proj_b[l]), h->y, H, M, H, H, LLB_ACT_NONE, false, s, ctr));
+        a.shift = mod, a.scale = mod + H, a.gate = mod + 2 * H;
+        LLB_TRY(launch_row_ln(a, s));
+      }
       h->launches++;
     }
     ctr->slot = LLB_PROF_GEMM_FC1;
@@ -513,12 +527,14 @@ static int dit_launch_step(llb_dit* h, DitStepArgs& a, cudaStream_t s) {
   const size_t smem = dit_step_smem(h->L.N, a.passes);
   static size_t configured = 0;
   if (smem > configured) {
-    LLB_CUDA_OK(cudaFuncSetAttribute(dit_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LLB_CUDA_OK(cudaFuncSetAttribute(dit_step_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LLB_CUDA_OK(cudaFuncSetAttribute(dit_step_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   {
     ProfScope prof(LLB_PROF_DIT_STEP, s);
-    dit_step_kernel<<<h->B, 256, smem, s>>>(a, h->tables);
+    if (h->B <= num_sms()) dit_step_kernel<512><<<h->B, 512, smem, s>>>(a, h->tables);   // fewer molecules than SMs: wider CTAs
+    else dit_step_kernel<256><<<h->B, 256, smem, s>>>(a, h->tables);
   }
   LLB_CUDA_OK(cudaGetLastError());
   h->launches++;
@@ -578,6 +594,7 @@ int llb_dit_pack_weights(const llb_dit_config* cfg, const llb_dit_weights* w, vo
     LLB_CUDA_OK(cp(L.kn_w[l], w->k_norm_w[l], DIT_DH));
     LLB_CUDA_OK(cp(L.kn_b[l], w->k_norm_b[l], DIT_DH));
     LLB_CUDA_OK(cp(L.proj_b[l], w->proj_b[l], H));
+    LLB_CUDA_OK(cudaMemsetAsync(static_cast<uint8_t*>(packed) + L.proj_b[l] + H * 4, 0, (size_t)H * 4, s));
     LLB_CUDA_OK(cp(L.fc1_b[l], w->fc1_b[l], F));
     LLB_CUDA_OK(cp(L.fc2_b[l], w->fc2_b[l], H));
     LLB_CUDA_OK(cudaMemsetAsync(static_cast<uint8_t*>(packed) + L.fc2_b[l] + H * 4, 0, (size_t)(LLB_DIT_SPLITK - 1) * H * 4, s));
@@ -791,3 +808,5 @@ int llb_dit_posterior_sample(llb_dit* h, int t, const float* lc_X, const float* 
 }
 
 }  // extern "C"
+
+LLB_STEP_TRACE_INSTALL(llb_trace_install_dit)

@@ -126,21 +126,26 @@ __device__ __forceinline__ uint32_t attt_swz(int row, int chunk) { return (uint3
 __global__ void __launch_bounds__(128) dit_attention_tma_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ out,
                                                                 const int32_t* __restrict__ mol_off, int B, int Mtok, int H, int heads) {
   pdl_launch_dependents();
-  pdl_wait();   // qkv comes from the previous kernel of the stream
+  LLB_STAMP(0x1A, 0, threadIdx.x == 0);
   __shared__ __align__(1024) uint8_t tiles[3 * ATTT_TILE];
   __shared__ __align__(8) uint64_t bar;
   const int head = blockIdx.x % heads;
   const int seq = blockIdx.x / heads;  // pass * B + molecule
   const int b = seq % B, pass = seq / B;
-  const int row0 = pass * Mtok + mol_off[b];
-  const int n = mol_off[b + 1] - mol_off[b];
-  if (n == 0) return;
+  // the molecule offsets are constants of the batch binding (copied in by llb_dit_begin): read, like the barrier set-up, ahead of
+  // the dependency wait
+  const int row0 = pass * Mtok + __ldg(mol_off + b);
+  const int n = __ldg(mol_off + b + 1) - __ldg(mol_off + b);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
+    tma_prefetch_desc(&tmQKV);
     mbar_init(&bar, 1);
     fence_mbar_init();
   }
   __syncthreads();
+  pdl_wait();   // qkv comes from the previous kernel of the stream
+  LLB_STAMP(0x2A, 0, threadIdx.x == 0);
+  if (n == 0) return;
   if (tid == 0) {
     mbar_arrive_expect_tx(&bar, 3 * ATTT_TILE);
 #pragma unroll
@@ -518,7 +523,11 @@ __device__ __forceinline__ float post_term(float v, float ux, float p, float pu,
 }
 
 // Dynamic shared memory: T[pass][n][d0] logits rows (fp32), then NodeStats[pass][n], then small arrays.
-__global__ void __launch_bounds__(256) dit_step_kernel(DitStepArgs a, const __grid_constant__ DitTablesDev tb) {
+// THREADS = 256 (two CTAs per SM at throughput batch sizes) or 512 (a handful of molecules: one CTA per molecule is all the
+// parallelism there is, so each gets more threads); every loop strides by blockDim.x.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) dit_step_kernel(DitStepArgs a, const __grid_constant__ DitTablesDev tb) {
+  LLB_STAMP(0x1C, 0, threadIdx.x == 0);
   extern __shared__ __align__(16) float sm[];
   const int b = blockIdx.x;
   const int N = a.N, d0 = DIT_XC + DIT_EC * N;

@@ -285,6 +285,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();   // the next kernel of the stream may begin its own prologue on SMs this grid leaves free
+  LLB_STAMP(0x10 + BN / 64, ((unsigned long long)N << 32) | (unsigned)K, threadIdx.x == 0);
 
   if (warp == GEMM_EPI_WARPS) {
     // ---------------- TMA producer: the whole warp walks the ring (uniform control flow), one elected lane issues ----------------
@@ -309,6 +310,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       __syncwarp();
     }
     pdl_wait();
+    LLB_STAMP(0x20 + BN / 64, ((unsigned long long)N << 32) | (unsigned)K, lane == 0);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (m_fast ? tile % num_m : tile / num_n) * GEMM_BM;
       const int n0 = (m_fast ? tile / num_m : tile % num_n) * BN;
@@ -349,6 +351,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t d_tmem = tmem_base + acc * BN;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full[stage], phase);
+        if (kb == 0 || kb == num_kb - 1) LLB_STAMP(kb == 0 ? 0x40 : 0x50, ((unsigned long long)N << 32) | (unsigned)K, lane == 0);
         tc_fence_after();
         if (elect_one()) {
           const uint64_t a_desc = a_desc0 + (uint64_t)(stage * (Cfg::A_BYTES >> 4));
@@ -383,6 +386,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const auto rst = gemm_epilogue_row_begin(epi, m0, M);
       gemm_stage_warp_vectors<BN>(epi, stg, n0, N);
       mbar_wait(&tmem_full[acc], acc_phase);
+      LLB_STAMP(0x60, ((unsigned long long)N << 32) | (unsigned)K, threadIdx.x == 0);
       tc_fence_after();
       gemm_epilogue_tile<BN, TMA_STORE>(epi, &tmC, tmem_base + acc * BN, m0, n0, M, N, stg, buf, rst);
       tc_fence_before();
@@ -393,10 +397,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         acc_phase ^= 1;
       }
     }
-    if (TMA_STORE && lane == 0) bulk_wait_all();
+    // the staging buffers must have been read before the CTA retires its shared memory; the global writes themselves are part of
+    // the grid's completion like any other store
+    if (TMA_STORE && lane == 0) bulk_wait_read<0>();
   }
   tc_fence_before();
   __syncthreads();
+  LLB_STAMP(0x30 + BN / 64, ((unsigned long long)N << 32) | (unsigned)K, threadIdx.x == 0);
   if (warp == GEMM_EPI_WARPS + 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -516,6 +523,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  LLB_STAMP(0x1D, ((unsigned long long)N << 32) | (unsigned)K, threadIdx.x == 0);
 
   if (warp == GEMM_EPI_WARPS) {
     // ---------------- TMA producer (both CTAs; completion bytes go to the leader's full[]) ----------------
@@ -633,6 +641,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     if (TMA_STORE && lane == 0) bulk_wait_all();
   }
   tc_fence_before();
+  LLB_STAMP(0x3D, ((unsigned long long)N << 32) | (unsigned)K, threadIdx.x == 0);
   cluster_sync_all();   // nobody leaves while the peer may still signal its barriers / read its operand half
   if (warp == GEMM_EPI_WARPS + 2) {
     tc_fence_after();

@@ -26,10 +26,6 @@ __device__ __forceinline__ uint32_t cluster_rank() {
   return r;
 }
 // One instruction pulls a whole (rows x cols) box of a tensor into L2.
-__device__ __forceinline__ void l2_prefetch_tile(const CUtensorMap* map, int c0, int c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1)
-               : "memory");
-}
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * GEMM_EPI_WARPS) : "memory"); }
 __device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
   asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");

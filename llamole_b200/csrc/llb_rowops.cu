@@ -117,10 +117,27 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 template <int NCH, unsigned F>
 __global__ void __launch_bounds__(256) row_ln_reg_kernel(RowLnDev a) {
   pdl_launch_dependents();   // the next kernel's prologue (and its weight prefetch) may overlap this memory-bound pass
-  pdl_wait();
+  LLB_STAMP(0x1B, a.in_parts, threadIdx.x == 0);
   constexpr bool RT = (F & F_RUNTIME) != 0;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  // Ahead of the dependency wait: the row's modulation vectors into L1.  They (and row_group) are constants of the step, written
+  // by a launch that is NOT programmatic and lies before this one in the stream, so they are complete whenever this kernel runs at
+  // all; the dependent round trips row_group -> vectors then overlap the tail of the GEMM this kernel waits for.
+  if (!RT && (F & F_MOD) && (F & F_GATE) && row < a.rows) {
+    const int g0 = a.row_group ? __ldg(a.row_group + row) : row;
+    const float* m0 = a.shift + (size_t)g0 * a.mod_ld + lane * 4;
+    const float* m1 = a.scale + (size_t)g0 * a.mod_ld + lane * 4;
+    const float* m2 = a.gate + (size_t)g0 * a.mod_ld + lane * 4;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(m0 + k * 128));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(m1 + k * 128));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(m2 + k * 128));
+    }
+  }
+  pdl_wait();
+  LLB_STAMP(0x2B, a.in_parts, threadIdx.x == 0);
   if (row >= a.rows) return;
   const bool in_bf16 = RT ? a.in_bf16 != 0 : (F & F_IN_BF16) != 0;
   const bool norm = RT ? a.normalize != 0 : (F & F_NORM) != 0;
@@ -137,11 +154,30 @@ __global__ void __launch_bounds__(256) row_ln_reg_kernel(RowLnDev a) {
   float4 v[NCH];
 #pragma unroll
   for (int k = 0; k < NCH; ++k) v[k] = load4(a.in, in_bf16, in_off + lane * 4 + k * 128);
-  for (int p = 1; p < a.in_parts; ++p) {   // split-K partial products, summed in index order
+  // split-K partial products, summed in index order
+  if (NCH <= 8 && (a.in_parts == 4 || a.in_parts == 2)) {   // all loads of the slices in flight together (one exposed round trip)
+    constexpr int NQ = NCH <= 8 ? NCH : 1;
+    float4 q[3][NQ];
+    const int extra = a.in_parts - 1;
 #pragma unroll
-    for (int k = 0; k < NCH; ++k) {
-      const float4 q = load4(a.in, in_bf16, in_off + (size_t)p * a.in_part_stride + lane * 4 + k * 128);
-      v[k].x += q.x, v[k].y += q.y, v[k].z += q.z, v[k].w += q.w;
+    for (int p = 0; p < 3; ++p)
+      if (p < extra) {
+#pragma unroll
+        for (int k = 0; k < NQ; ++k) q[p][k] = load4(a.in, in_bf16, in_off + (size_t)(p + 1) * a.in_part_stride + lane * 4 + k * 128);
+      }
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+      if (p < extra) {
+#pragma unroll
+        for (int k = 0; k < NQ; ++k) v[k].x += q[p][k].x, v[k].y += q[p][k].y, v[k].z += q[p][k].z, v[k].w += q[p][k].w;
+      }
+  } else {
+    for (int p = 1; p < a.in_parts; ++p) {
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) {
+        const float4 q = load4(a.in, in_bf16, in_off + (size_t)p * a.in_part_stride + lane * 4 + k * 128);
+        v[k].x += q.x, v[k].y += q.y, v[k].z += q.z, v[k].w += q.w;
+      }
     }
   }
   // the residual is fetched together with the row (one exposed DRAM latency per row)
@@ -329,3 +365,5 @@ int launch_linear_f32(const float* in, int in_ld, const float* W, int w_ld, cons
 }
 
 }  // namespace llb
+
+LLB_STEP_TRACE_INSTALL(llb_trace_install_rowops)

@@ -282,3 +282,5 @@ int llb_gemm_bf16(const void* A, int lda, const void* W, int ldw, const float* b
 }
 
 }  // extern "C"
+
+LLB_STEP_TRACE_INSTALL(llb_trace_install_runtime)
