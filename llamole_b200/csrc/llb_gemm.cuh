@@ -704,7 +704,9 @@ int launch_gemm(const void* A, int lda, const void* W, int ldw, int M, int N, in
   static bool configured[4] = {false, false, false, false};  // per template instantiation
   // CTA-pair kernel: wide problems whose 256 x 256 pair-tiles fill the machine
   const int pair_tiles = ceil_div(M, 2 * GEMM_BM) * ceil_div(N, 256);
-  const bool use_pair = BN == 256 && pair_tiles >= num_sms() / 2 && grp.group_n % 256 == 0;
+  // (not for a single row block: the pair's second CTA would multiply nothing but padding, and a skinny GEMM -- the adaLN
+  // modulations of a handful of molecules, 352 MB of weights against 7 rows -- wants every SM streaming its own weight tiles)
+  const bool use_pair = BN == 256 && M > GEMM_BM && pair_tiles >= num_sms() / 2 && grp.group_n % 256 == 0;
   if (use_pair) {
     CUtensorMap tmBh;
     LLB_TRY(make_tensor_map_2d(&tmBh, W, 2, w_rows, w_cols, ldw, GEMM_BK, 128, 128));
