@@ -597,6 +597,8 @@ def bench_latency(args, m, eng, device, local_rank, pk, T):
     """Latency regime (BASELINE.json configs[0]: B = 16; the reference's own call pattern: B = 6 = per_device_eval_batch_size of
     config/generate/*.yaml, modeling_llamole.py:653).  Measured BEFORE the throughput section: a handful of molecules never reaches
     the power cap, so the SM clock of this measurement should not be the capped one the long step leaves behind."""
+    from llamole_b200 import synth
+
     if args.small:
         return None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
