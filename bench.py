@@ -329,6 +329,19 @@ def main():
         barrier()
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     comm_ms = max_over_ranks(evc.elapsed_time(ev1)) if world > 1 else 0.0
+    comm_alone_ms = 0.0
+    if world > 1:
+        # inside the timed region the gather also absorbs the SKEW between the ranks (GPUs under the power cap differ by a few per cent
+        # over a ~0.7 s region); the exchange on its own, from a barrier: pack + all-gather + unpack
+        barrier()
+        torch.cuda.synchronize()
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
+        Xs, Es = eng.get_state()
+        sharding.unpack_graphs(sharding.all_gather_rows(sharding.pack_graphs(Xs, Es, n_dev, check=False), sizes=[B] * world), N)
+        eb.record()
+        torch.cuda.synchronize()
+        comm_alone_ms = max_over_ranks(ea.elapsed_time(eb))
     prof = _cabi.profile_read()
     _cabi.profile_enable(False)
     dit_launches = eng.launch_count() - launches0
@@ -438,8 +451,11 @@ def main():
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic", "config": workload_config(args), "clocks": clocks.summary(), "e2e": e2e,
             "comm": {"backend": "nccl" if world > 1 else None, "nranks": world, "comm_ms": comm_ms, "comm_ms_per_step": comm_ms / args.steps,
+                     "comm_alone_ms": comm_alone_ms,
                      "what": "one all-gather of the packed sampled graphs (sharding.pack_graphs, 1327 B/molecule) + unpack, once per sampling run; "
-                             "included in ms_per_step" if world > 1 else "single GPU: no exchange"},
+                             "comm_ms = from the last step's end to the gathered result inside the timed region (included in ms_per_step; it "
+                             "absorbs the skew between the ranks), comm_alone_ms = the same exchange timed from a barrier" if world > 1
+                             else "single GPU: no exchange"},
             "latency": latency, "sampling_kernel": step_kernel,
             "gpu_launches": int(dit_launches + gin.pop("_launches") + (pred.pop("_launches") if pred else 0)), "roofline": roofline,
             "cpu_baseline": cpu, "kernel_breakdown": breakdown, "ragged": ragged, "gin": gin, "predictor": pred,
