@@ -62,10 +62,10 @@ const char* llb_profile_slot_name(int slot);
 enum {
   LLB_KERN_GEMM_1CTA = 0,    /* gemm_tcgen05_kernel */
   LLB_KERN_GEMM_2CTA,        /* gemm_tcgen05_2cta_kernel (cta_group::2) */
-  LLB_KERN_GEMM_LN_PAIR,     /* gemm_ln_pair_kernel */
-  LLB_KERN_GEMM_LN_CLUSTER,  /* gemm_ln_cluster_kernel */
-  LLB_KERN_GIN_FUSED_MLP,    /* gin_mlp_fused_kernel (aggregation-fed GEMM chain of a GIN layer) */
-  LLB_KERN_HEAD_TOPK,        /* gemm_head_topk_kernel (predictor head GEMM + online softmax + top-k) */
+  LLB_KERN_GEMM_LN_PAIR,     /* gemm_ln_pair_kernel<..., GIN = 0>: GraphDiT block tail (GEMM + LayerNorm + modulation + residual) */
+  LLB_KERN_GEMM_LN_CLUSTER,  /* retired in round 2 (the thread-block-cluster variant of the above); always 0, slot kept for ABI stability */
+  LLB_KERN_GIN_FUSED_MLP,    /* gemm_ln_pair_kernel<..., GIN = 1>: second GIN linear + LayerNorm + layer tail + max-pooling */
+  LLB_KERN_HEAD_TOPK,        /* gemm_tcgen05_2cta_kernel<EpiHeadTopk>: predictor head GEMM + softmax partial sums + top-k candidates */
   LLB_KERN_FAMILIES
 };
 int64_t llb_kernel_launches(int family);
