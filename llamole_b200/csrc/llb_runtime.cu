@@ -175,18 +175,21 @@ int make_tensor_map_2d(CUtensorMap* out, const void* ptr, int elem_bytes, int ro
   return LLB_OK;
 }
 
-// Pick the N tile: fewest "tile-column units" per SM wave, with a mild preference for the wide tile.
-static int pick_bn(int M, int N, int group_n = 0) {
+// Pick the N tile of the single-CTA kernel by a small time model (clocks per CTA, measured in the latency regime,
+// profiles/r2_latency_timeline.txt): a tile's k-loop issues K/16 MMAs, each taking max(95, BN/2) clocks -- one tcgen05.mma of
+// M = 128 is accepted every ~95 clocks however narrow it is, so halving the tile does NOT halve its time --, its epilogue and
+// hand-over cost ~600 + 6 BN, and the tiles run in ceil(tiles / SMs) rounds.
+static int pick_bn(int M, int N, int K, int group_n = 0) {
   const int sms = num_sms();
   const int mt = ceil_div(M, GEMM_BM);
   int best = 256;
   double best_cost = 1e30;
   const int cand[3] = {256, 128, 64};
-  const double ineff[3] = {1.0, 1.08, 1.3};
   for (int i = 0; i < 3; ++i) {
     if (group_n > 0 && group_n % cand[i] != 0) continue;   // a tile must not straddle two groups
     const int tiles = mt * ceil_div(N, cand[i]);
-    const double cost = (double)ceil_div(tiles, sms) * cand[i] * ineff[i];
+    const double per_mma = cand[i] / 2 > 95 ? cand[i] / 2 : 95;
+    const double cost = (double)ceil_div(tiles, sms) * (ceil_div(K, 16) * per_mma + 600.0 + 6.0 * cand[i]);
     if (cost < best_cost) {
       best_cost = cost;
       best = cand[i];
@@ -200,7 +203,7 @@ static int gemm_dispatch_bn(const void* A, int lda, const void* W, int ldw, cons
                             int N, int K, cudaStream_t stream, GemmCounters* ctr, GemmGroups grp) {
   LLB_CHECK_ARG(bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0, "gemm: bias must be 16-byte aligned");
   EpiBiasAct<ACT, F32> epi{C, ldc, bias};
-  switch (pick_bn(M, N, grp.group_n)) {
+  switch (pick_bn(M, N, K, grp.group_n)) {
     case 256: return launch_gemm<256>(A, lda, W, ldw, M, N, K, epi, stream, ctr, grp);
     case 128: return launch_gemm<128>(A, lda, W, ldw, M, N, K, epi, stream, ctr, grp);
     default: return launch_gemm<64>(A, lda, W, ldw, M, N, K, epi, stream, ctr, grp);
