@@ -469,11 +469,19 @@ static bool dit_graph_enabled() {
 // instantiate it; the executable graph is then launched into the caller's stream.
 static int dit_build_graph(llb_dit* h) {
   h->graph_state = -1;
-  if (!h->capture_stream) LLB_CUDA_OK(cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking));
+  // a capture that cannot even begin (the caller is capturing this thread's work itself, say) is not an error of the pass either
+  if (!h->capture_stream && cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    (void)cudaGetLastError();
+    h->capture_stream = nullptr;
+    return LLB_OK;
+  }
   int64_t kern0[LLB_KERN_FAMILIES];
   for (int f = 0; f < LLB_KERN_FAMILIES; ++f) kern0[f] = llb_kernel_launches(f);
   const int64_t own0 = h->launches, gemm0 = h->ctr.launches;
-  LLB_CUDA_OK(cudaStreamBeginCapture(h->capture_stream, cudaStreamCaptureModeThreadLocal));
+  if (cudaStreamBeginCapture(h->capture_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return LLB_OK;
+  }
   const int rc = dit_body(h, h->capture_stream);
   cudaGraph_t g = nullptr;
   const cudaError_t e = cudaStreamEndCapture(h->capture_stream, &g);
