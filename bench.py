@@ -240,6 +240,7 @@ def main():
     ap.add_argument("--no-predictor", action="store_true")
     ap.add_argument("--small", action="store_true", help="tiny model (debug only; invalid as a benchmark)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true", help="skip the small-batch latency section (profiler captures of the throughput step)")
     ap.add_argument("--only", default="", choices=["", "gin", "predictor"], help="development: time one GIN sub-benchmark alone and print its object")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -289,7 +290,7 @@ def main():
     # ------------------------------------------------------------------ GraphDiT
     m, cfg, meta, sd = build_dit(device, small=args.small)
     eng = m.engine()
-    latency = bench_latency(args, m, eng, device, local_rank, pk, T)
+    latency = None if args.no_latency else bench_latency(args, m, eng, device, local_rank, pk, T)
     B = args.dit_batch
     N = m.max_n_nodes
     props_h, txt_h = synth.dit_conditions(B, seed=2024 + rank)
