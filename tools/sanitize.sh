@@ -17,3 +17,9 @@ for tool in memcheck synccheck; do
   echo "$tool rc=$?" >> $out/sanitizer_${tool}_big_$tag.log
   tail -4 $out/sanitizer_${tool}_big_$tag.log
 done
+# the latency regime: CUDA-graph replay, programmatic dependent launches (prefetches ahead of the dependency wait), split-K + row kernel
+for tool in memcheck synccheck; do
+  timeout 900 compute-sanitizer --tool $tool --print-limit 20 --error-exitcode 99 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "graph_replay or full_size_logits or degenerate" > $out/sanitizer_${tool}_lat_$tag.log 2>&1
+  echo "$tool rc=$?" >> $out/sanitizer_${tool}_lat_$tag.log
+  tail -4 $out/sanitizer_${tool}_lat_$tag.log
+done
