@@ -1,6 +1,6 @@
-// Debug probe (not part of the product): phase timeline of the fused GEMM + LayerNorm cluster kernel.
+// Debug probe (not part of the product): phase timeline of the fused GEMM + LayerNorm CTA-pair kernel (GraphDiT block tails).
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --expt-relaxed-constexpr -DLLB_GEMM_TRACE -I. \
-//        tools/gemm_ln_trace.cu llamole_b200/csrc/llb_gemm_ln.cu llamole_b200/csrc/llb_runtime.cu -o tools/gemm_ln_trace.bin
+//        tools/gemm_ln_trace.cu llamole_b200/csrc/llb_gemm_ln.cu llamole_b200/csrc/llb_runtime.cu llamole_b200/csrc/llb_rowops.cu -lcuda -o tools/gemm_ln_trace.bin
 #include <vector>
 #include "../llamole_b200/csrc/llb_gemm_ln.cuh"
 using namespace llb;
@@ -23,13 +23,12 @@ int main() {
   void* ws; const size_t wsb = gemm_ln_pair_workspace_bytes(); cudaMalloc(&ws, wsb);
   const int nexp = 3;
   const int exps[nexp] = {0, 3, 16};
-  for (int pairmode = 1; pairmode < 2; ++pairmode)
   for (int xi = 0; xi < nexp; ++xi)
   for (int K : {1024, 4096}) {
     llb_gln_set_exp(exps[xi]);
-    printf("=== %s kernel, knock-out mask %d (1 no x store, 2 no xb store, 4 no residual reload, 8 no pass 2, 16 empty epilogue)\n", pairmode ? "pair" : "cluster", exps[xi]);
+    printf("=== pair kernel, knock-out mask %d (1 no x store, 2 no xb store, 4 no residual reload, 8 no pass 2, 16 empty epilogue)\n", exps[xi]);
     GemmLnArgs e{bias, grp, mod, mod + N, mod + 2 * N, 6 * N, x, N, xb, N};
-    auto launch = [&]() { return pairmode ? launch_gemm_ln_pair(A, K, W, K, M, N, K, e, ws, wsb, 0, nullptr) : launch_gemm_ln(A, K, W, K, M, N, K, e, 0, nullptr); };
+    auto launch = [&]() { return launch_gemm_ln_pair(A, K, W, K, M, N, K, e, ws, wsb, 0, nullptr); };
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0), cudaEventCreate(&e1);
     for (int i = 0; i < 2; ++i)
