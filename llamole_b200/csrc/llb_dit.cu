@@ -358,6 +358,7 @@ static int dit_body(llb_dit* h, cudaStream_t s) {
   }
   const bool attn_umma = attn_env == 2 && L.heads % 2 == 0;
   const bool fused_pair = fused_ln;
+  const size_t part_rows = (size_t)(M < 640 ? M : 640) * LLB_DIT_SPLITK;   // rows x slices the split-K buffer h->part holds (dit_carve)
   const size_t ln_sync_bytes = gemm_ln_pair_workspace_bytes();
   for (int l = 0; l < D; ++l) {
     const float* mod = h->mod + (size_t)l * 6 * H;   // row stride ldm
@@ -407,7 +408,8 @@ static int dit_body(llb_dit* h, cudaStream_t s) {
       // latency regime: K = H in two slices (twice the CTAs streaming the weight, half the k-blocks each: the k-loop is paced by
       // the bytes one SM's TMA ring can take, 406 rows: 16 blocks 3.0 us), partial products summed by the row kernel
       static const bool no_splitk_p = getenv("LLB_SPLITK") && getenv("LLB_SPLITK")[0] == '0';
-      if (latency_regime && !no_splitk_p && M <= 640 && H % 128 == 0 && ceil_div(M, 128) * (2 * H / 64) <= num_sms()) {
+      // (while the two slices' 128-wide tiles fit one wave -- up to 9 row blocks -- and the slice buffer)
+      if (latency_regime && !no_splitk_p && H % 128 == 0 && ceil_div(M, 128) * (2 * H / 128) <= num_sms() && 2 * (size_t)M <= part_rows) {
         GemmGroups grp;
         grp.group_n = H, grp.group_k = H / 2, grp.split_k = true;
         LLB_TRY(gemm_bias_act(h->attn, H, h->w<void>(L.proj_w[l]), H, h->w<float>(L.proj_b[l]), h->part, 2 * H, M, 2 * H, H / 2, LLB_ACT_NONE, true, s,
@@ -433,16 +435,22 @@ static int dit_body(llb_dit* h, cudaStream_t s) {
       // latency regime: K = F is cut into LLB_DIT_SPLITK slices that run as groups of one launch (4x the CTAs streaming the
       // weights, a quarter of the k-blocks each); the row kernel adds the fp32 partial products in slice order
       static const bool no_splitk = getenv("LLB_SPLITK") && getenv("LLB_SPLITK")[0] == '0';
-      const int Ks = F / LLB_DIT_SPLITK;
-      // measured: 406 rows 2.16 -> 2.05 ms/step, 978 rows 2.40 -> 2.42 (enough row tiles to fill the machine already)
-      const bool splitk = latency_regime && !no_splitk && F % LLB_DIT_SPLITK == 0 && Ks % 64 == 0 && H % 128 == 0 && M <= 640;
-      if (splitk) {
+      // four slices up to 640 rows (measured: 406 rows 2.16 -> 2.05 ms/step); beyond that four slices no longer fit one wave
+      // (978 rows: 2.40 -> 2.42) but TWO do up to 9 row blocks, and a CTA's k-loop is paced by its K / 16 MMA issues (256 of them
+      // for the whole K at 978 rows: the long pole of the block)
+      int parts = 1;
+      if (latency_regime && !no_splitk && H % 128 == 0) {
+        if (M <= 640 && F % (LLB_DIT_SPLITK * 64) == 0) parts = LLB_DIT_SPLITK;
+        else if (F % 128 == 0 && ceil_div(M, 128) * (2 * H / 128) <= num_sms() && 2 * (size_t)M <= part_rows) parts = 2;
+      }
+      const int Ks = F / parts;
+      if (parts > 1) {
         GemmGroups grp;
         grp.group_n = H, grp.group_k = Ks, grp.split_k = true;
-        LLB_TRY(gemm_bias_act(h->hbuf, F, h->w<void>(L.fc2_w[l]), F, h->w<float>(L.fc2_b[l]), h->part, LLB_DIT_SPLITK * H, M, LLB_DIT_SPLITK * H,
+        LLB_TRY(gemm_bias_act(h->hbuf, F, h->w<void>(L.fc2_w[l]), F, h->w<float>(L.fc2_b[l]), h->part, parts * H, M, parts * H,
                               Ks, LLB_ACT_NONE, true, s, ctr, grp));
         RowLnArgs ap = a;
-        ap.in = h->part, ap.in_ld = LLB_DIT_SPLITK * H, ap.in_bf16 = false, ap.in_parts = LLB_DIT_SPLITK, ap.in_part_stride = H;
+        ap.in = h->part, ap.in_ld = parts * H, ap.in_bf16 = false, ap.in_parts = parts, ap.in_part_stride = H;
         ap.shift = mod + 3 * H, ap.scale = mod + 4 * H, ap.gate = mod + 5 * H;
         LLB_TRY(launch_row_ln(ap, s));
       } else {

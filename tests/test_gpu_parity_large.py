@@ -101,15 +101,20 @@ def dit_wide():
     return m.to(DEV), cfg, meta, sd
 
 
-def test_dit_wide_batch_vs_oracle(dit_wide):
+@pytest.mark.parametrize("B,low,regime", [(48, 30, "throughput"), (12, 40, "latency")])
+def test_dit_wide_batch_vs_oracle(dit_wide, B, low, regime):
+    """H = 1024 denoiser against the fp32 oracle at two sizes: >= 2048 token rows (CTA-pair GEMMs, fused GEMM + LayerNorm tails) and
+    ~1000 rows, the upper end of the latency regime (single-CTA GEMMs, proj / fc2 as TWO K-slices summed by the row kernel, the
+    second pass replayed as a CUDA graph)."""
     from oracle import llamole_oracle as O
 
     m, cfg, meta, sd = dit_wide
-    B, N, T = 48, 50, cfg["diffusion_steps"]
+    N, T = 50, cfg["diffusion_steps"]
     gen = torch.Generator().manual_seed(12)
-    n_nodes = torch.randint(30, 51, (B,), generator=gen)
-    n_nodes[0], n_nodes[1] = 50, 30
-    assert 2 * int(n_nodes.sum()) >= 2048
+    n_nodes = torch.randint(low, 51, (B,), generator=gen)
+    n_nodes[0], n_nodes[1] = 50, low
+    rows = 2 * int(n_nodes.sum())
+    assert rows >= 2048 if regime == "throughput" else 640 < rows <= 1152, rows
     props, txt = synth.dit_conditions(B, seed=31)
     props[3, 5] = -200.0    # a missing property in an otherwise complete row
     y = torch.where(props == -200.0, torch.full_like(props, float("nan")), props)
@@ -141,9 +146,14 @@ def test_dit_wide_batch_vs_oracle(dit_wide):
             assert torch.equal(lE, lE.transpose(1, 2))
         qX, qE = ex(B, N, 16), ex(B, N, N, 5)
         Xn, En, _, _, pX, pE = O.reverse_step(sd, cfg, tb, U, sched, X, E, node_mask, y, txt, t, qX, qE, return_probs=True)
-    assert _cabi.kernel_launches(_cabi.KERN_GEMM_2CTA) > k2, "qkv / fc1 must have run on the CTA-pair GEMM"
-    if os.environ.get("LLB_FUSED_LN") != "0":
-        assert _cabi.kernel_launches(_cabi.KERN_GEMM_LN_PAIR) > kp, "the block tails must have run on the fused GEMM + LayerNorm pair kernel"
+    if regime == "throughput":
+        assert _cabi.kernel_launches(_cabi.KERN_GEMM_2CTA) > k2, "qkv / fc1 must have run on the CTA-pair GEMM"
+        if os.environ.get("LLB_FUSED_LN") != "0":
+            assert _cabi.kernel_launches(_cabi.KERN_GEMM_LN_PAIR) > kp, "the block tails must have run on the fused GEMM + LayerNorm pair kernel"
+    else:
+        assert _cabi.kernel_launches(_cabi.KERN_GEMM_LN_PAIR) == kp, "the latency regime uses GEMM + row kernel tails"
+        if os.environ.get("LLB_GRAPH") != "0" and "LLB_FUSED_LN" not in os.environ:   # (that switch also leaves the latency regime)
+            assert eng.graph_state() == 1, "the second pass of the binding must have been replayed as a graph"
     print(f"\n[parity] denoiser at {2 * int(n_nodes.sum())} token rows (H=1024, depth 3) vs fp32 oracle: max|d|={worst[0]:.4f} rms={worst[1]:.5f}")
     assert worst[0] <= 0.10 and worst[1] <= 0.02, worst
     # full reverse step with the same pre-drawn noise: categories agree wherever the oracle's margin exceeds the propagated
@@ -164,7 +174,7 @@ def test_dit_wide_batch_vs_oracle(dit_wide):
     assert bool(eqx[mX > gate].all()) and bool(eqe[mE > gate].all()), (gate, float(eqx.float().mean()), float(eqe.float().mean()))
     agree = (int(eqx.sum()) + int(eqe.sum())) / (eqx.numel() + eqe.numel())
     dp = float((gpX.cpu() - pX)[node_mask].abs().max())
-    record_parity("dit_wide_batch_vs_oracle", token_rows=2 * int(n_nodes.sum()), depth=3, hidden=1024, logits_max_abs=worst[0], logits_rms=worst[1],
+    record_parity("dit_wide_batch_vs_oracle" if regime == "throughput" else "dit_latency_regime_1000_rows_vs_oracle", token_rows=2 * int(n_nodes.sum()), depth=3, hidden=1024, logits_max_abs=worst[0], logits_rms=worst[1],
                   category_gate=gate, category_agreement=agree, max_prob_diff=dp,
                   smallest_margin_of_a_disagreement=float(torch.cat([mX[~eqx], mE[~eqe], torch.tensor([float("inf")])]).min()),
                   largest_margin_of_a_disagreement=float(torch.cat([mX[~eqx], mE[~eqe], torch.tensor([0.0])]).max()))
