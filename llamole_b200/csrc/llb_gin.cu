@@ -235,10 +235,12 @@ __global__ void __launch_bounds__(256) gin_aggregate_kernel(const float* __restr
   for (int c = lane * 8; c < H; c += 256) {
     float acc[8];
     {
-      const float4 a = *reinterpret_cast<const float4*>(h + (size_t)i * H + c);
-      const float4 b = *reinterpret_cast<const float4*>(h + (size_t)i * H + c + 4);
-      acc[0] = one_eps * a.x, acc[1] = one_eps * a.y, acc[2] = one_eps * a.z, acc[3] = one_eps * a.w;
-      acc[4] = one_eps * b.x, acc[5] = one_eps * b.y, acc[6] = one_eps * b.z, acc[7] = one_eps * b.w;
+      // the self term comes from the bf16 copy as well: the sum is rounded to bf16 on the way out anyway (same error scale), the
+      // row is the one this node's neighbours gather (L2-resident), and the fp32 row it replaces was a quarter of the kernel's
+      // DRAM reads
+      const uint4 a = *reinterpret_cast<const uint4*>(hb + (size_t)i * H + c);
+      acc[0] = one_eps * bf16_lo(a.x), acc[1] = one_eps * bf16_hi(a.x), acc[2] = one_eps * bf16_lo(a.y), acc[3] = one_eps * bf16_hi(a.y);
+      acc[4] = one_eps * bf16_lo(a.z), acc[5] = one_eps * bf16_hi(a.z), acc[6] = one_eps * bf16_lo(a.w), acc[7] = one_eps * bf16_hi(a.w);
     }
     for (int k = beg; k < end; ++k) {
       const int j = __ldg(col + k);
