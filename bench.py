@@ -696,7 +696,7 @@ def bench_gin(args, device, rank, world, barrier, max_over_ranks, pk):
         "value": world * G / (ms / 1e3), "unit": "graphs/s", "ms_per_forward": ms, "graphs_per_gpu": G, "nodes": n, "directed_edges": e,
         "config": {"hidden": H, "layers": L, "timed": "CSR build (llb_gin_bind) + GraphCLIP forward, inputs resident in HBM"},
         "e2e": {"value": world * G / (e2e_ms / 1e3), "unit": "graphs/s", "h2d_bytes_per_step": (n * 2 + e * 3) * 8, "d2h_bytes_per_step": G * H * 4},
-        "roofline": {"bound": "hbm", "kernel": "gin_aggregate_kernel", "achieved": agg_bytes / (agg_ms / 1e3) / 1e9, "peak": pk["hbm"],
+        "roofline": {"bound": "hbm", "kernel": "gin_aggregate_wide_kernel", "achieved": agg_bytes / (agg_ms / 1e3) / 1e9, "peak": pk["hbm"],
                      "unit": "GB/s", "frac": agg_bytes / (agg_ms / 1e3) / 1e9 / pk["hbm"], "traffic": ncu_traffic("gin_aggregate"), "launch_ms": agg_ms,
                      "bytes_per_launch": agg_bytes, "peak_source": pk["source"]},
         "mlp_gemms": {"tflops": mlp_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms else None, "frac_of_sustained": mlp_flops / (gemm_ms / 1e3) / 1e12 / pk["tf_sustained"] if gemm_ms else None,

@@ -221,8 +221,54 @@ __global__ void gin_broadcast_rows_kernel(const float* __restrict__ row, float* 
 }
 
 // GIN aggregation (graph_encoder/model.py:167-173): out_i = (1+eps) h_i + sum_{j->i} gelu(h_j + bond_emb[e_ji]) -> bf16.
-// One warp per destination node, 8 columns (16 B of bf16) per lane per sweep; CSR rows are short (degree <= ~4).
-__global__ void __launch_bounds__(256) gin_aggregate_kernel(const float* __restrict__ h, const __nv_bfloat16* __restrict__ hb,
+// One warp per destination node, 8 columns (16 B of bf16) per lane per sweep; CSR rows are short (degree <= ~4).  The self term is
+// read from the bf16 copy (the row the node's neighbours gather anyway; the sum is rounded to bf16 on the way out).  This is the
+// any-width fallback (H a multiple of 8); H = 256, 512, 768, 1024 go to gin_aggregate_wide_kernel.
+// Width-specialised variant (H = 256 NSW): the neighbour loop is the OUTER one, so a neighbour's index / bond type are read once
+// and its NSW 16-byte gathers are in flight together (three loads per lane instead of one when H = 768); 8 NSW fp32 accumulators.
+template <int NSW>
+__global__ void __launch_bounds__(256) gin_aggregate_wide_kernel(const __nv_bfloat16* __restrict__ hb, const int32_t* __restrict__ rowptr,
+                                                                 const int32_t* __restrict__ col, const int32_t* __restrict__ eid,
+                                                                 const float* __restrict__ bond_emb, const float* __restrict__ eps_ptr,
+                                                                 __nv_bfloat16* __restrict__ out, int n) {
+  constexpr int H = 256 * NSW;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= n) return;
+  const float one_eps = 1.0f + __ldg(eps_ptr);
+  const int beg = rowptr[i], end = rowptr[i + 1];
+  float acc[NSW][8];
+#pragma unroll
+  for (int w = 0; w < NSW; ++w) {
+    const uint4 a = *reinterpret_cast<const uint4*>(hb + (size_t)i * H + w * 256 + lane * 8);
+    acc[w][0] = one_eps * bf16_lo(a.x), acc[w][1] = one_eps * bf16_hi(a.x), acc[w][2] = one_eps * bf16_lo(a.y), acc[w][3] = one_eps * bf16_hi(a.y);
+    acc[w][4] = one_eps * bf16_lo(a.z), acc[w][5] = one_eps * bf16_hi(a.z), acc[w][6] = one_eps * bf16_lo(a.w), acc[w][7] = one_eps * bf16_hi(a.w);
+  }
+  for (int k = beg; k < end; ++k) {
+    const int j = __ldg(col + k);
+    const int et = __ldg(eid + k) & 7;
+    const __nv_bfloat16* src = hb + (size_t)j * H + lane * 8;
+    const float* emb = bond_emb + (size_t)et * H + lane * 8;
+    uint4 u[NSW];
+#pragma unroll
+    for (int w = 0; w < NSW; ++w) u[w] = *reinterpret_cast<const uint4*>(src + w * 256);
+#pragma unroll
+    for (int w = 0; w < NSW; ++w) {
+      const float4 e0 = __ldg(reinterpret_cast<const float4*>(emb + w * 256));
+      const float4 e1 = __ldg(reinterpret_cast<const float4*>(emb + w * 256 + 4));
+      acc[w][0] += gelu_bf16(bf16_lo(u[w].x) + e0.x), acc[w][1] += gelu_bf16(bf16_hi(u[w].x) + e0.y);
+      acc[w][2] += gelu_bf16(bf16_lo(u[w].y) + e0.z), acc[w][3] += gelu_bf16(bf16_hi(u[w].y) + e0.w);
+      acc[w][4] += gelu_bf16(bf16_lo(u[w].z) + e1.x), acc[w][5] += gelu_bf16(bf16_hi(u[w].z) + e1.y);
+      acc[w][6] += gelu_bf16(bf16_lo(u[w].w) + e1.z), acc[w][7] += gelu_bf16(bf16_hi(u[w].w) + e1.w);
+    }
+  }
+#pragma unroll
+  for (int w = 0; w < NSW; ++w)
+    *reinterpret_cast<uint4*>(out + (size_t)i * H + w * 256 + lane * 8) = make_uint4(
+        pack_bf16x2(acc[w][0], acc[w][1]), pack_bf16x2(acc[w][2], acc[w][3]), pack_bf16x2(acc[w][4], acc[w][5]), pack_bf16x2(acc[w][6], acc[w][7]));
+}
+
+__global__ void __launch_bounds__(256) gin_aggregate_kernel(const __nv_bfloat16* __restrict__ hb,
                                                             const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                                                             const int32_t* __restrict__ eid, const float* __restrict__ bond_emb,
                                                             const float* __restrict__ eps_ptr, __nv_bfloat16* __restrict__ out,
@@ -1148,8 +1194,16 @@ static int gin_trunk(llb_gin* g, const float* c, cudaStream_t s) {
     const bool last = (l == L - 1);
     {
       ProfScope prof(LLB_PROF_GIN_AGGREGATE, s);
-      gin_aggregate_kernel<<<ceil_div(n, 8), 256, 0, s>>>(g->h, g->hb, g->rowptr, g->col, g->eid, g->w<float>(G.bond_emb[l]),
-                                                          g->w<float>(G.eps[l]), g->agg, n, H);
+      const float* be = g->w<float>(G.bond_emb[l]);
+      const float* ep = g->w<float>(G.eps[l]);
+      const unsigned blocks = (unsigned)ceil_div(n, 8);
+      switch (H) {   // width-specialised (neighbour-outer) kernel for the widths the checkpoints and fixtures use
+        case 256: gin_aggregate_wide_kernel<1><<<blocks, 256, 0, s>>>(g->hb, g->rowptr, g->col, g->eid, be, ep, g->agg, n); break;
+        case 512: gin_aggregate_wide_kernel<2><<<blocks, 256, 0, s>>>(g->hb, g->rowptr, g->col, g->eid, be, ep, g->agg, n); break;
+        case 768: gin_aggregate_wide_kernel<3><<<blocks, 256, 0, s>>>(g->hb, g->rowptr, g->col, g->eid, be, ep, g->agg, n); break;
+        case 1024: gin_aggregate_wide_kernel<4><<<blocks, 256, 0, s>>>(g->hb, g->rowptr, g->col, g->eid, be, ep, g->agg, n); break;
+        default: gin_aggregate_kernel<<<blocks, 256, 0, s>>>(g->hb, g->rowptr, g->col, g->eid, be, ep, g->agg, n, H);
+      }
     }
     LLB_CUDA_OK(cudaGetLastError());
     g->launches++;
