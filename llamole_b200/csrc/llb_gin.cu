@@ -482,15 +482,18 @@ __global__ void gin_f32_to_f16_kernel(const float* __restrict__ src, __half* __r
 
 // Per-graph pooling over the contiguous node range (graph_encoder/model.py:148,152): max -> bf16 operand of the
 // virtual-node MLP, sum -> fp32 (+bf16) read-out.  grid (B, ceil(H/256)).
-__global__ void __launch_bounds__(256) gin_pool_kernel(const float* __restrict__ h, const int32_t* __restrict__ graph_ptr, int H,
-                                                       int is_max, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16) {
+// hb != null: read the bf16 copy of the rows instead (max-pooling into a bf16 result only: rounding is monotone, so the maximum of
+// the rounded values IS the rounded maximum -- same bits, half the bytes).
+__global__ void __launch_bounds__(256) gin_pool_kernel(const float* __restrict__ h, const __nv_bfloat16* __restrict__ hb,
+                                                       const int32_t* __restrict__ graph_ptr, int H, int is_max, float* __restrict__ out_f32,
+                                                       __nv_bfloat16* __restrict__ out_bf16) {
   const int g = blockIdx.x;
   const int c = blockIdx.y * 256 + threadIdx.x;
   if (c >= H) return;
   const int beg = graph_ptr[g], end = graph_ptr[g + 1];
   float acc = is_max ? -INFINITY : 0.f;
   for (int i = beg; i < end; ++i) {
-    const float v = h[(size_t)i * H + c];
+    const float v = hb ? __bfloat162float(hb[(size_t)i * H + c]) : h[(size_t)i * H + c];
     acc = is_max ? fmaxf(acc, v) : acc + v;
   }
   if (beg == end) acc = 0.f;
@@ -1219,7 +1222,7 @@ static int gin_trunk(llb_gin* g, const float* c, cudaStream_t s) {
           const size_t total = (size_t)B * H;
           gin_pool_decode_kernel<<<(unsigned)(ceil_div((int)(total / 4), 256) < 2048 ? ceil_div((int)(total / 4), 256) : 2048), 256, 0, s>>>(g->pool_enc, g->pool_b, total);
         } else {
-          gin_pool_kernel<<<dim3(B, ceil_div(H, 256)), 256, 0, s>>>(g->h, g->graph_ptr, H, 1, nullptr, g->pool_b);
+          gin_pool_kernel<<<dim3(B, ceil_div(H, 256)), 256, 0, s>>>(nullptr, g->hb, g->graph_ptr, H, 1, nullptr, g->pool_b);
         }
       }
       LLB_CUDA_OK(cudaGetLastError());
@@ -1275,7 +1278,7 @@ static int gin_trunk(llb_gin* g, const float* c, cudaStream_t s) {
   }
   {
     ProfScope prof(LLB_PROF_GIN_POOL, s);
-    gin_pool_kernel<<<dim3(B, ceil_div(H, 256)), 256, 0, s>>>(g->h, g->graph_ptr, H, 0, g->pooled, g->pooled_b);
+    gin_pool_kernel<<<dim3(B, ceil_div(H, 256)), 256, 0, s>>>(g->h, nullptr, g->graph_ptr, H, 0, g->pooled, g->pooled_b);
   }
   LLB_CUDA_OK(cudaGetLastError());
   g->launches++;
