@@ -501,6 +501,24 @@ __global__ void __launch_bounds__(256) gin_pool_kernel(const float* __restrict__
   if (out_bf16) out_bf16[(size_t)g * H + c] = __float2bfloat16(acc);
 }
 
+// Max-pool of the bf16 copy, two columns per thread (H even): rounding is monotone, so the maximum of the rounded values IS the
+// rounded maximum of the fp32 rows -- same bits as gin_pool_kernel on h, half the bytes.  grid (B, ceil(H/512)).
+__global__ void __launch_bounds__(256) gin_pool_max_bf16_kernel(const __nv_bfloat16* __restrict__ hb, const int32_t* __restrict__ graph_ptr,
+                                                                int H, __nv_bfloat16* __restrict__ out) {
+  const int g = blockIdx.x;
+  const int c = (blockIdx.y * 256 + threadIdx.x) * 2;
+  if (c >= H) return;
+  const int beg = graph_ptr[g], end = graph_ptr[g + 1];
+  float a0 = -INFINITY, a1 = -INFINITY;
+#pragma unroll 4
+  for (int i = beg; i < end; ++i) {
+    const uint32_t u = *reinterpret_cast<const uint32_t*>(hb + (size_t)i * H + c);
+    a0 = fmaxf(a0, bf16_lo(u)), a1 = fmaxf(a1, bf16_hi(u));
+  }
+  if (beg == end) a0 = a1 = 0.f;
+  *reinterpret_cast<uint32_t*>(out + (size_t)g * H + c) = pack_bf16x2(a0, a1);
+}
+
 // Per-graph maxima accumulated by the fused layer tail (order-preserving uint encoding, 0 = no node seen) -> bf16 operand of
 // the virtual-node MLP.
 __global__ void gin_pool_decode_kernel(const uint32_t* __restrict__ enc, __nv_bfloat16* __restrict__ out, size_t total) {
@@ -1222,7 +1240,8 @@ static int gin_trunk(llb_gin* g, const float* c, cudaStream_t s) {
           const size_t total = (size_t)B * H;
           gin_pool_decode_kernel<<<(unsigned)(ceil_div((int)(total / 4), 256) < 2048 ? ceil_div((int)(total / 4), 256) : 2048), 256, 0, s>>>(g->pool_enc, g->pool_b, total);
         } else {
-          gin_pool_kernel<<<dim3(B, ceil_div(H, 256)), 256, 0, s>>>(nullptr, g->hb, g->graph_ptr, H, 1, nullptr, g->pool_b);
+          if (H % 2 == 0) gin_pool_max_bf16_kernel<<<dim3(B, ceil_div(H, 512)), 256, 0, s>>>(g->hb, g->graph_ptr, H, g->pool_b);
+          else gin_pool_kernel<<<dim3(B, ceil_div(H, 256)), 256, 0, s>>>(nullptr, g->hb, g->graph_ptr, H, 1, nullptr, g->pool_b);
         }
       }
       LLB_CUDA_OK(cudaGetLastError());
