@@ -25,11 +25,7 @@ __device__ __forceinline__ uint32_t cluster_rank() {
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
 }
-// One instruction pulls a whole (rows x cols) box of a tensor into L2.
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * GEMM_EPI_WARPS) : "memory"); }
-__device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
-  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
-}
 
 struct GlnPass2 {
   uint32_t t_row;        // TMEM address of this warp's first column

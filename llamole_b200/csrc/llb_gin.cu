@@ -616,7 +616,6 @@ __global__ void __launch_bounds__(1024) gin_topk_kernel(const float* __restrict_
 // redoes it -- with strided ownership that needs 4 of the top k in one of 1024 residue classes.  Order: value
 // descending, ties to the lowest index, like the selection-pass kernel.
 constexpr int TK_T = 4;
-__device__ __forceinline__ bool tk_before(float v, int i, float w, int j) { return v > w || (v == w && i < j); }
 
 __global__ void __launch_bounds__(1024) gin_topk_stream_kernel(const float* __restrict__ logits, int ld, int W, int k,
                                                                float* __restrict__ topv, int32_t* __restrict__ topi,
@@ -624,9 +623,6 @@ __global__ void __launch_bounds__(1024) gin_topk_stream_kernel(const float* __re
   if (only_flagged && redo_flag[blockIdx.x] == 0) return;   // the threshold kernel already produced this row
   __shared__ float red_v[32];
   __shared__ float red_s[32];
-  __shared__ int red_i[32];
-  __shared__ float s_v;
-  __shared__ int s_i;
   __shared__ float s_max, s_sum;
   __shared__ int s_redo;
   const float* row = logits + (size_t)blockIdx.x * ld;
