@@ -67,6 +67,12 @@ template <class T>
 struct pdl_ident {
   using type = T;
 };
+// Set to make the NEXT launch_pdl of this thread an ordinary launch (a full dependency on everything before it in the stream):
+// what some later kernel reads AHEAD of its own dependency wait must have been produced before such a launch.
+inline bool& pdl_full_barrier_next() {
+  static thread_local bool flag = false;
+  return flag;
+}
 template <class... KArgs>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, typename pdl_ident<KArgs>::type... args) {
   cudaLaunchConfig_t cfg = {};
@@ -74,7 +80,8 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = s;
-  cfg.attrs = attr, cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr, cfg.numAttrs = (pdl_enabled() && !pdl_full_barrier_next()) ? 1 : 0;
+  pdl_full_barrier_next() = false;
   return cudaLaunchKernelEx(&cfg, kern, args...);
 }
 

@@ -367,11 +367,16 @@ static int dit_body(llb_dit* h, cudaStream_t s) {
     const bool share0 = l == 0 && h->passes == 2 && fused_ln;
     ctr->slot = LLB_PROF_GEMM_QKV;
     EpiQKV eq{h->qkv, 3 * H, H, h->w<float>(L.qn_w[l]), h->w<float>(L.qn_b[l]), h->w<float>(L.kn_w[l]), h->w<float>(L.kn_b[l]), q_scale};
+    // The first kernel of the blocks is launched the ordinary way: the row kernels prefetch their modulation vectors AHEAD of
+    // their dependency wait, and with a full dependency here everything the adaLN GEMMs wrote is complete before any kernel of a
+    // block can run any code at all -- by construction, not by the SMs happening to be full.
+    if (l == 0) pdl_full_barrier_next() = true;
     // latency regime: 128-wide tiles while they fit one wave (twice the CTAs streaming the weight, half the MMAs per CTA)
     if (latency_regime && ceil_div(M, 128) * ceil_div(3 * H, 128) <= num_sms())
       LLB_TRY((launch_gemm<128>(h->xb, H, h->w<void>(L.qkv_w[l]), H, M, 3 * H, H, eq, s, ctr)));
     else
       LLB_TRY((launch_gemm<256>(h->xb, H, h->w<void>(L.qkv_w[l]), H, share0 ? Mtok : M, 3 * H, H, eq, s, ctr)));
+    pdl_full_barrier_next() = false;   // (the CTA-pair kernel is launched the ordinary way anyway and does not consume the flag)
     {
       const int seqs = (share0 ? 1 : h->passes) * B;
       CUtensorMap tmQKV;
